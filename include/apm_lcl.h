@@ -1,0 +1,134 @@
+/*
+ * apm_lcl.h -- C ABI of libapmlcl.so, the B200-native local-cubic-law (LCL) flow solve.
+ *
+ * Drop-in boundary for the hot path of stadelmanma/netl-ap-map-flow.  The reference crosses a
+ * PROCESS boundary here: apmapflow/run_model/run_model.py:752-759 Popen()s
+ * `apm-lcl-model.exe <file.inp>` (apmapflow/src/APERTURE_MAP_FLOW.F:1-51).  This library is what a
+ * ctypes binding replaces that Popen with.  No torch / C++ types cross the boundary: plain
+ * pointers, sizes and PODs.  Every pointer that carries map data may be a HOST or a DEVICE pointer
+ * (row-major [nz][nx] doubles, row 0 = first line of the map file = bottom of the fracture,
+ * APERTURE_MAP_FLOW.F:448-449, cell index I=(IZ-1)*NX+IX :491-497); the library inspects it with
+ * cudaPointerGetAttributes and copies only when needed.
+ *
+ * All functions return 0 on success and 1 on failure (the reference's exit status,
+ * APERTURE_MAP_FLOW.F:47-49); apm_lcl_last_error() returns the message (thread local).
+ * There is no CPU fallback: without a CUDA device every compute entry point fails.
+ */
+#ifndef APM_LCL_H
+#define APM_LCL_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define APM_LCL_VERSION 100
+
+/* OUTLET-SIDE, matched by substring in this order (APM_MODULE.F:306-368) */
+enum { APM_LCL_LEFT = 0, APM_LCL_RIGHT = 1, APM_LCL_TOP = 2, APM_LCL_BOTTOM = 3 };
+
+/* Model parameters in SI / voxel units exactly as READ_MASTER leaves them
+ * (APERTURE_MAP_FLOW.F:88-126 defaults, :226-384 keywords). */
+typedef struct apm_lcl_params {
+    double inlet_pressure;   /* INLPB  [Pa]; < 0 = not supplied (default -1)            */
+    double outlet_pressure;  /* OUTPB  [Pa]; < 0 = not supplied                         */
+    double inlet_rate;       /* INJRATE [m^3/s]; <= 0 = not supplied                    */
+    double outlet_rate;      /* OUTRATE [m^3/s]; <= 0 = not supplied                    */
+    double density;          /* RHO [kg/m^3]                                            */
+    double viscosity;        /* AVG_VISC [Pa s], must be > 0                            */
+    double voxel_size;       /* VOX_MET [m per voxel]                                   */
+    double avg_factor;       /* AVG_FACT, MAP AVERAGING FACTOR                          */
+    double roughness;        /* R_FACT [voxels]                                         */
+    double high_mask;        /* HIGH_MASK [voxels]                                      */
+    double low_mask;         /* LOW_MASK [voxels]                                       */
+    int    outlet_side;      /* APM_LCL_LEFT/RIGHT/TOP/BOTTOM                           */
+    /* solver controls (new; the reference's direct D4 solve has none) */
+    double rel_tol;          /* stop when ||r||2/||b||2 AND ||D^-1/2 r||/||D^-1/2 b|| <= rel_tol; <=0 -> 1e-10 */
+    int    max_iter;         /* <=0 -> 500                                              */
+    int    flags;            /* reserved, 0                                             */
+} apm_lcl_params;
+
+/* Per-cell outputs, SI units, each nz*nx doubles or NULL to skip (host or device pointers).
+ * APERTURE_MAP_FLOW.F:825-869 before the output-unit conversion. */
+typedef struct apm_lcl_fields {
+    double *pressure;   /* PRES  = FRAC_PR(1:NZ,1:NX)                                    */
+    double *flow_x;     /* QX_OUT = Q2 (Q1 if outlet LEFT)                               */
+    double *flow_z;     /* QZ_OUT = Q4 (Q3 if outlet BOTTOM)                             */
+    double *flow_m;     /* QM_OUT = sqrt(QX^2+QZ^2)                                      */
+    double *aperture;   /* WIDTH (roughness-adjusted, clamped, metres)                   */
+    double *reynolds;   /* REN = rho/mu * QM / WIDTH                                     */
+    double *residual;   /* RES = |Q5| / max|Q5|                                          */
+} apm_lcl_fields;
+
+typedef struct apm_lcl_scalars {
+    /* READ_AP_MAP counters (bit exact) and averages, APERTURE_MAP_FLOW.F:472-480 */
+    long long zeros;         /* COUNT(INT(A*1E9)==0)                                    */
+    long long masked;        /* COUNT(A>HIGH)+COUNT(A<LOW)                              */
+    double raw_aper;         /* mean aperture before masking [voxels]                   */
+    double avg_aper;         /* mean aperture after masking [m]                         */
+    double min_aper;         /* MINVAL(A, A>0) [voxels]                                 */
+    double max_aper;         /* MAXVAL(A) [voxels]                                      */
+    /* results */
+    double inlet_pressure;   /* INLPB after the solve (rate BC back-fill :680-688) [Pa]  */
+    double outlet_pressure;  /* OUTPB after the solve [Pa]                               */
+    double flow;             /* signed FLOW = sum over outlet cells (:850-857) [m^3/s]   */
+    double outlet_rate;      /* OUTRATE = |FLOW|                                         */
+    double max_residual;     /* Q5 at MAXLOC(|Q5|) (signed, :879)                        */
+    /* solver diagnostics */
+    int    iterations;       /* PCG iterations (sum over solves)                         */
+    int    converged;        /* 1 if both stopping tests passed                          */
+    double rel_residual;     /* final ||r||2/||b||2 (true residual)                      */
+    double rel_residual_scaled; /* final ||D^-1/2 r||2/||D^-1/2 b||2                     */
+    double setup_ms;         /* conductances + multigrid hierarchy (device time)         */
+    double solve_ms;         /* PCG (device time)                                        */
+    double total_ms;         /* aperture-on-device -> outputs-on-device                  */
+} apm_lcl_scalars;
+
+typedef struct apm_lcl_solver apm_lcl_solver;   /* opaque, owns all device scratch */
+
+int         apm_lcl_version(void);
+const char *apm_lcl_last_error(void);
+/* number of kernels launched by this thread's last compute call (bench.py's gpu_launches) */
+long long   apm_lcl_last_launch_count(void);
+
+/* Defaults of INITIALIZE_RUN (APERTURE_MAP_FLOW.F:88-126). */
+void apm_lcl_default_params(apm_lcl_params *p);
+
+/* Persistent solver for maps of one size on one device.  Replaces ALLOCATE_FRAC
+ * (APM_MODULE.F:107-123) + INIT_SOLVER (D4_SOLVER_MODULE.F:110-139). */
+int apm_lcl_solver_create(apm_lcl_solver **out, int device, int nx, int nz);
+int apm_lcl_solver_destroy(apm_lcl_solver *s);
+
+/* The hot path: READ_AP_MAP numeric core -> CREATE_POINT_MAP -> COEF -> FLOW_BOUNDARY ->
+ * SOLVER -> FRAC_FLOW -> OUTPUT_DATA derived fields (APERTURE_MAP_FLOW.F:472-501, 597-693,
+ * 700-767, 815-869; APM_MODULE.F:142-376; MAP_MODULE.F:91-176).  The direct D4 solve
+ * (D4_SOLVER_MODULE.F:444-617) is replaced by multigrid-preconditioned CG on the same system. */
+int apm_lcl_solver_solve(apm_lcl_solver *s, const apm_lcl_params *p, const double *aperture,
+                         apm_lcl_fields *out, apm_lcl_scalars *sc);
+
+/* One-shot convenience (create + solve + destroy) on `device`. */
+int apm_lcl_solve(const apm_lcl_params *p, const double *aperture, int nx, int nz, int device,
+                  apm_lcl_fields *out, apm_lcl_scalars *sc);
+
+/* Kernel-level entry points used by the parity tests -------------------------------------- */
+
+/* COEF + FLOW_BOUNDARY: writes WIDTH[nz*nx], TRX[nz][nx+1] (faces 0..NX of each row) and
+ * TRZ[nz+1][nx] (faces 0..NZ) in the reference's indexing (APM_MODULE.F:118), any may be NULL. */
+int apm_lcl_conductance(const apm_lcl_params *p, const double *aperture, int nx, int nz, int device,
+                        double *width, double *trx, double *trz, apm_lcl_scalars *sc);
+
+/* Access to the most recent solve's device-resident state (for roofline benches): returns
+ * device pointers owned by the solver, valid until the next solve/destroy. */
+int apm_lcl_solver_device_field(apm_lcl_solver *s, const char *name, double **ptr, size_t *count);
+
+/* Times ONE kernel of the solve on the solver's current state, `reps` back-to-back launches on the
+ * solver's stream bracketed by CUDA events.  name: "spmv", "update", "direction", "smooth_down",
+ * "smooth_up", "vcycle", "conductance", "flux".  Returns average ms per launch in *ms and the
+ * kernel's algorithmic bytes per launch in *bytes. */
+int apm_lcl_solver_time_kernel(apm_lcl_solver *s, const char *name, int reps, double *ms, double *bytes);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* APM_LCL_H */

@@ -25,6 +25,12 @@ extern "C" {
 
 #define APM_LCL_VERSION 100
 
+#if defined(__GNUC__)
+#define APM_LCL_API __attribute__((visibility("default")))
+#else
+#define APM_LCL_API
+#endif
+
 /* OUTLET-SIDE, matched by substring in this order (APM_MODULE.F:306-368) */
 enum { APM_LCL_LEFT = 0, APM_LCL_RIGHT = 1, APM_LCL_TOP = 2, APM_LCL_BOTTOM = 3 };
 
@@ -87,46 +93,46 @@ typedef struct apm_lcl_scalars {
 
 typedef struct apm_lcl_solver apm_lcl_solver;   /* opaque, owns all device scratch */
 
-int         apm_lcl_version(void);
-const char *apm_lcl_last_error(void);
+APM_LCL_API int         apm_lcl_version(void);
+APM_LCL_API const char *apm_lcl_last_error(void);
 /* number of kernels launched by this thread's last compute call (bench.py's gpu_launches) */
-long long   apm_lcl_last_launch_count(void);
+APM_LCL_API long long   apm_lcl_last_launch_count(void);
 
 /* Defaults of INITIALIZE_RUN (APERTURE_MAP_FLOW.F:88-126). */
-void apm_lcl_default_params(apm_lcl_params *p);
+APM_LCL_API void apm_lcl_default_params(apm_lcl_params *p);
 
 /* Persistent solver for maps of one size on one device.  Replaces ALLOCATE_FRAC
  * (APM_MODULE.F:107-123) + INIT_SOLVER (D4_SOLVER_MODULE.F:110-139). */
-int apm_lcl_solver_create(apm_lcl_solver **out, int device, int nx, int nz);
-int apm_lcl_solver_destroy(apm_lcl_solver *s);
+APM_LCL_API int apm_lcl_solver_create(apm_lcl_solver **out, int device, int nx, int nz);
+APM_LCL_API int apm_lcl_solver_destroy(apm_lcl_solver *s);
 
 /* The hot path: READ_AP_MAP numeric core -> CREATE_POINT_MAP -> COEF -> FLOW_BOUNDARY ->
  * SOLVER -> FRAC_FLOW -> OUTPUT_DATA derived fields (APERTURE_MAP_FLOW.F:472-501, 597-693,
  * 700-767, 815-869; APM_MODULE.F:142-376; MAP_MODULE.F:91-176).  The direct D4 solve
  * (D4_SOLVER_MODULE.F:444-617) is replaced by multigrid-preconditioned CG on the same system. */
-int apm_lcl_solver_solve(apm_lcl_solver *s, const apm_lcl_params *p, const double *aperture,
+APM_LCL_API int apm_lcl_solver_solve(apm_lcl_solver *s, const apm_lcl_params *p, const double *aperture,
                          apm_lcl_fields *out, apm_lcl_scalars *sc);
 
 /* One-shot convenience (create + solve + destroy) on `device`. */
-int apm_lcl_solve(const apm_lcl_params *p, const double *aperture, int nx, int nz, int device,
+APM_LCL_API int apm_lcl_solve(const apm_lcl_params *p, const double *aperture, int nx, int nz, int device,
                   apm_lcl_fields *out, apm_lcl_scalars *sc);
 
 /* Kernel-level entry points used by the parity tests -------------------------------------- */
 
 /* COEF + FLOW_BOUNDARY: writes WIDTH[nz*nx], TRX[nz][nx+1] (faces 0..NX of each row) and
  * TRZ[nz+1][nx] (faces 0..NZ) in the reference's indexing (APM_MODULE.F:118), any may be NULL. */
-int apm_lcl_conductance(const apm_lcl_params *p, const double *aperture, int nx, int nz, int device,
+APM_LCL_API int apm_lcl_conductance(const apm_lcl_params *p, const double *aperture, int nx, int nz, int device,
                         double *width, double *trx, double *trz, apm_lcl_scalars *sc);
 
 /* Access to the most recent solve's device-resident state (for roofline benches): returns
  * device pointers owned by the solver, valid until the next solve/destroy. */
-int apm_lcl_solver_device_field(apm_lcl_solver *s, const char *name, double **ptr, size_t *count);
+APM_LCL_API int apm_lcl_solver_device_field(apm_lcl_solver *s, const char *name, double **ptr, size_t *count);
 
 /* Times ONE kernel of the solve on the solver's current state, `reps` back-to-back launches on the
  * solver's stream bracketed by CUDA events.  name: "spmv", "update", "direction", "smooth_down",
  * "smooth_up", "vcycle", "conductance", "flux".  Returns average ms per launch in *ms and the
  * kernel's algorithmic bytes per launch in *bytes. */
-int apm_lcl_solver_time_kernel(apm_lcl_solver *s, const char *name, int reps, double *ms, double *bytes);
+APM_LCL_API int apm_lcl_solver_time_kernel(apm_lcl_solver *s, const char *name, int reps, double *ms, double *bytes);
 
 #ifdef __cplusplus
 }

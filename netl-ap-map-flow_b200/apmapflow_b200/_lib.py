@@ -92,6 +92,12 @@ def load():
             "libapmlcl.so not found at %s -- build it with `python -c 'import __graft_entry__ as g; "
             "g.build()'` (nvcc, sm_100a). There is no CPU fallback." % LIB_PATH)
     lib = C.CDLL(LIB_PATH, mode=C.RTLD_GLOBAL)
+    _lib = bind(lib)
+    return _lib
+
+
+def bind(lib):
+    """Attach the prototypes of include/apm_lcl.h to a loaded library object."""
     lib.apm_lcl_version.restype = C.c_int
     lib.apm_lcl_last_error.restype = C.c_char_p
     lib.apm_lcl_last_launch_count.restype = C.c_longlong
@@ -109,7 +115,6 @@ def load():
                                                 C.POINTER(C.c_size_t)]
     lib.apm_lcl_solver_time_kernel.argtypes = [C.c_void_p, C.c_char_p, C.c_int,
                                                C.POINTER(C.c_double), C.POINTER(C.c_double)]
-    _lib = lib
     return lib
 
 

@@ -1,0 +1,448 @@
+// api.cu -- the C ABI of libapmlcl.so (include/apm_lcl.h) and the solve driver.
+//
+// The driver is the device-side counterpart of the reference's INITIALIZE_RUN -> FRAC_FLOW ->
+// OUTPUT_DATA sequence (apmapflow/src/APERTURE_MAP_FLOW.F:28-42), restricted to its numeric core.
+#include <cmath>
+#include <cstring>
+#include <limits>
+
+#include "common.cuh"
+
+namespace lcl {
+
+thread_local std::string g_last_error;
+thread_local long long g_launches = 0;
+
+static bool is_device_ptr(const void *p)
+{
+    if (!p) return false;
+    cudaPointerAttributes a{};
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
+static void alloc_d(double **p, size_t count) { CUDA_CHECK(cudaMalloc((void **)p, (count ? count : 1) * sizeof(double))); }
+
+static void solver_free(Solver *s)
+{
+    if (!s) return;
+    cudaSetDevice(s->device);
+    mg_free(*s);
+    double *ptrs[] = {s->ap, s->width, s->tx, s->tz, s->txl, s->tzb, s->x, s->r, s->d, s->q, s->z, s->red, s->scal};
+    for (double *p : ptrs)
+        if (p) cudaFree(p);
+    if (s->red_counters) cudaFree(s->red_counters);
+    if (s->state) cudaFree(s->state);
+    if (s->state_host) cudaFreeHost(s->state_host);
+    if (s->scal_host) cudaFreeHost(s->scal_host);
+    for (auto &e : s->ev)
+        if (e) cudaEventDestroy(e);
+    if (s->stream) cudaStreamDestroy(s->stream);
+    delete s;
+}
+
+static Solver *solver_new(int device, int nx, int nz)
+{
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) {
+        cudaGetLastError();
+        throw CudaError{"no CUDA device available: libapmlcl has no CPU fallback"};
+    }
+    if (device < 0 || device >= count) throw CudaError{"invalid CUDA device index"};
+    if (nx < 1 || nz < 1) throw CudaError{"map dimensions must be >= 1"};
+    CUDA_CHECK(cudaSetDevice(device));
+    Solver *s = new Solver();
+    try {
+        s->device = device; s->nx = nx; s->nz = nz; s->n = (size_t)nx * nz;
+        cudaDeviceProp prop{};
+        CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
+        s->num_sms = prop.multiProcessorCount;
+        CUDA_CHECK(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+        double **fields[] = {&s->ap, &s->width, &s->tx, &s->tz, &s->x, &s->r, &s->d, &s->q, &s->z};
+        for (auto f : fields) alloc_d(f, s->n);
+        alloc_d(&s->txl, nz);
+        alloc_d(&s->tzb, nx);
+        alloc_d(&s->red, (size_t)32 * kMaxPartials);
+        alloc_d(&s->scal, 64);
+        CUDA_CHECK(cudaMalloc((void **)&s->red_counters, 16 * sizeof(unsigned int)));
+        CUDA_CHECK(cudaMemset(s->red_counters, 0, 16 * sizeof(unsigned int)));
+        CUDA_CHECK(cudaMalloc((void **)&s->state, sizeof(PcgState)));
+        CUDA_CHECK(cudaMallocHost((void **)&s->state_host, sizeof(PcgState)));
+        CUDA_CHECK(cudaMallocHost((void **)&s->scal_host, 64 * sizeof(double)));
+        for (auto &e : s->ev) CUDA_CHECK(cudaEventCreate(&e));
+        mg_allocate(*s);
+    } catch (...) {
+        solver_free(s);
+        throw;
+    }
+    return s;
+}
+
+// sum over one side's boundary faces of T_b (P_b - p_i): the flow entering through that side
+__global__ void k_side_inflow(Fine5 v, const double *__restrict__ p, int side, double pb, double *out)
+{
+    __shared__ double sh[256];
+    const int nz = v.nz, nx = v.nx;
+    const int count = (side == APM_LCL_LEFT || side == APM_LCL_RIGHT) ? nz : nx;
+    double acc = 0.0;
+    for (int k = threadIdx.x; k < count; k += blockDim.x) {
+        double t, pi;
+        if (side == APM_LCL_LEFT) { t = v.txl[k]; pi = p[(size_t)k * nx]; }
+        else if (side == APM_LCL_RIGHT) { t = v.tx[(size_t)k * nx + nx - 1]; pi = p[(size_t)k * nx + nx - 1]; }
+        else if (side == APM_LCL_BOTTOM) { t = v.tzb[k]; pi = p[k]; }
+        else { t = v.tz[(size_t)(nz - 1) * nx + k]; pi = p[(size_t)(nz - 1) * nx + k]; }
+        acc += t * (pb - pi);
+    }
+    sh[threadIdx.x] = acc;
+    __syncthreads();
+    for (int o = blockDim.x / 2; o > 0; o >>= 1) {
+        if ((int)threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *out = sh[0];
+}
+
+__global__ void k_fill(double *x, size_t n, double v)
+{
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) x[i] = v;
+}
+
+static int opposite(int side)
+{
+    switch (side) {
+    case APM_LCL_LEFT: return APM_LCL_RIGHT;
+    case APM_LCL_RIGHT: return APM_LCL_LEFT;
+    case APM_LCL_TOP: return APM_LCL_BOTTOM;
+    default: return APM_LCL_TOP;
+    }
+}
+
+static BoundaryValues halo_values(int outlet_side, double inl, double out)
+{
+    // FRAC_FLOW: the outlet side gets OUTPB, the three other sides INLPB (APERTURE_MAP_FLOW.F:729-749)
+    BoundaryValues bv{inl, inl, inl, inl};
+    if (outlet_side == APM_LCL_LEFT) bv.left = out;
+    else if (outlet_side == APM_LCL_RIGHT) bv.right = out;
+    else if (outlet_side == APM_LCL_TOP) bv.top = out;
+    else bv.bottom = out;
+    return bv;
+}
+
+static void copy_out(Solver &s, double *dst, const double *src_dev, size_t count)
+{
+    if (!dst || dst == src_dev) return;
+    CUDA_CHECK(cudaMemcpyAsync(dst, src_dev, count * sizeof(double),
+                               is_device_ptr(dst) ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, s.stream));
+}
+
+static void validate(const apm_lcl_params &p)
+{
+    if (!(p.viscosity > 0)) throw CudaError{" ERROR - NONE OR INVAILD VISCOSITY PROVIDED"};
+    if (p.outlet_side < 0 || p.outlet_side > 3) throw CudaError{" INVALID OUTLET SIDE ENTERED"};
+    if (!(p.voxel_size > 0) || !(p.avg_factor > 0)) throw CudaError{"voxel size and averaging factor must be > 0"};
+}
+
+static const double *stage_aperture(Solver &s, const double *aperture)
+{
+    if (!aperture) throw CudaError{"aperture pointer is NULL"};
+    if (is_device_ptr(aperture)) return aperture;
+    CUDA_CHECK(cudaMemcpyAsync(s.ap, aperture, s.n * sizeof(double), cudaMemcpyHostToDevice, s.stream));
+    return s.ap;
+}
+
+static void read_map_scalars(Solver &s, const apm_lcl_params &p, apm_lcl_scalars *sc)
+{
+    CUDA_CHECK(cudaMemcpyAsync(s.scal_host, s.scal, 16 * sizeof(double), cudaMemcpyDeviceToHost, s.stream));
+    CUDA_CHECK(cudaStreamSynchronize(s.stream));
+    if (!sc) return;
+    const double cells = (double)s.nx * (double)s.nz;
+    sc->zeros = (long long)s.scal_host[SC_ZEROS];
+    sc->masked = (long long)s.scal_host[SC_MASKED];
+    sc->raw_aper = s.scal_host[SC_RAW_SUM] / cells;                    // APERTURE_MAP_FLOW.F:472
+    sc->avg_aper = s.scal_host[SC_CLAMP_SUM] / cells * p.voxel_size;   // :480
+    sc->min_aper = s.scal_host[SC_MIN_POS];
+    sc->max_aper = s.scal_host[SC_MAX];
+}
+
+static void do_solve(Solver &s, const apm_lcl_params &p, const double *aperture, apm_lcl_fields *out, apm_lcl_scalars *sc)
+{
+    validate(p);
+    CUDA_CHECK(cudaSetDevice(s.device));
+    g_launches = 0;
+    const double rel_tol = p.rel_tol > 0 ? p.rel_tol : 1e-10;
+    const int max_iter = p.max_iter > 0 ? p.max_iter : 500;
+    apm_lcl_scalars local{};
+    if (!sc) sc = &local;
+    std::memset(sc, 0, sizeof(*sc));
+
+    const double *ap_dev = stage_aperture(s, aperture);
+    CUDA_CHECK(cudaEventRecord(s.ev[0], s.stream));
+    launch_conductance(s, p, ap_dev);
+    mg_setup(s);
+    CUDA_CHECK(cudaEventRecord(s.ev[1], s.stream));
+
+    // boundary-condition mode (APERTURE_MAP_FLOW.F:137-143, 644-659)
+    const bool has_in = p.inlet_pressure >= 0, has_out = p.outlet_pressure >= 0;
+    const bool rate_in = p.inlet_rate > 0, rate_out = p.outlet_rate > 0;
+    double inl = p.inlet_pressure, outp = p.outlet_pressure;
+    const int side = p.outlet_side, in_side = opposite(side);
+    int rc_iters = 0;
+    if (has_in && has_out && !rate_in && !rate_out) {
+        rc_iters = pcg_solve(s, halo_values(side, inl, outp), rel_tol, max_iter, sc);
+    } else if ((has_out && !has_in && rate_in && !rate_out) || (has_in && !has_out && rate_out && !rate_in)) {
+        // Group-node (flow rate) BC, D4_SOLVER_MODULE.F:263-328, by linearity: the group side is an
+        // equipotential, so solve once with it at P0+1 and the pressure side at P0 (here P0 := 0),
+        // measure the side flow K, then scale:  sum_i T_i (P_g - p_i) = rate  =>  P_g - P0 = rate / K.
+        const bool inlet_group = rate_in;
+        const int gside = inlet_group ? in_side : side;
+        BoundaryValues bv = inlet_group ? halo_values(side, 1.0, 0.0) : halo_values(side, 0.0, 1.0);
+        rc_iters = pcg_solve(s, bv, rel_tol, max_iter, sc);
+        if (rc_iters >= 0) {
+            LAUNCH(k_side_inflow, 1, 256, 0, s.stream, s.view5(), (const double *)s.x, gside, 1.0, s.scal + 20);
+            CUDA_CHECK(cudaMemcpyAsync(s.scal_host + 20, s.scal + 20, sizeof(double), cudaMemcpyDeviceToHost, s.stream));
+            CUDA_CHECK(cudaStreamSynchronize(s.stream));
+            const double K = s.scal_host[20];
+            const double p0 = inlet_group ? outp : inl;
+            const double rate = inlet_group ? p.inlet_rate : -p.outlet_rate;
+            const double scale = rate / K;
+            launch_affine(s, s.x, s.n, scale, p0);
+            if (inlet_group) inl = p0 + scale; else outp = p0 + scale;   // APERTURE_MAP_FLOW.F:680-688
+        }
+    } else {
+        // e.g. both pressures AND a rate: the reference puts the group row on Dirichlet cells,
+        // NEUMANNG_CC = 0, and produces NaNs (SURVEY 8a quirk viii).  We refuse instead of solving.
+        throw CudaError{"INVALID BOUNDARY CONDITIONS: supply both pressures, or one pressure and the "
+                        "flow rate of the opposite side"};
+    }
+    if (rc_iters < 0) throw CudaError{g_last_error};
+    CUDA_CHECK(cudaEventRecord(s.ev[2], s.stream));
+
+    // fluxes + derived fields
+    apm_lcl_fields none{};
+    if (!out) out = &none;
+    const BoundaryValues bvf = halo_values(side, inl, outp);
+    FluxOut fo{};
+    double *scratch[5] = {s.r, s.d, s.q, s.z, s.ap};
+    double *user[5] = {out->flow_x, out->flow_z, out->flow_m, out->reynolds, out->residual};
+    double **slot[5] = {&fo.qx, &fo.qz, &fo.qm, &fo.ren, &fo.res};
+    for (int k = 0; k < 5; k++)
+        *slot[k] = user[k] ? (is_device_ptr(user[k]) ? user[k] : scratch[k]) : nullptr;
+    if (fo.res == s.ap && ap_dev == s.ap) { /* the staged copy is dead after the conductance pass */ }
+    launch_flux(s, p, s.x, bvf, fo);
+    CUDA_CHECK(cudaEventRecord(s.ev[3], s.stream));
+    for (int k = 0; k < 5; k++) copy_out(s, user[k], *slot[k], s.n);
+    copy_out(s, out->pressure, s.x, s.n);
+    copy_out(s, out->aperture, s.width, s.n);
+    CUDA_CHECK(cudaEventRecord(s.ev[4], s.stream));
+    read_map_scalars(s, p, sc);   // synchronises the stream
+
+    sc->inlet_pressure = inl;
+    sc->outlet_pressure = outp;
+    sc->flow = s.scal_host[SC_FLOW];
+    sc->outlet_rate = std::fabs(sc->flow);                 // :858
+    sc->max_residual = s.scal_host[SC_MAXRES_SIGNED];
+    float ms = 0;
+    CUDA_CHECK(cudaEventElapsedTime(&ms, s.ev[0], s.ev[1])); sc->setup_ms = ms;
+    CUDA_CHECK(cudaEventElapsedTime(&ms, s.ev[1], s.ev[2])); sc->solve_ms = ms;
+    CUDA_CHECK(cudaEventElapsedTime(&ms, s.ev[0], s.ev[4])); sc->total_ms = ms;
+    s.have_solution = true;
+    s.last_params = p;
+    if (!sc->converged) {
+        char buf[256];
+        snprintf(buf, sizeof buf, "PCG did not reach rel_tol %.3g in %d iterations (residual %.3e, scaled %.3e)",
+                 rel_tol, sc->iterations, sc->rel_residual, sc->rel_residual_scaled);
+        throw CudaError{buf};
+    }
+}
+
+}   // namespace lcl
+
+// =================================================================================== C ABI
+using namespace lcl;
+
+struct apm_lcl_solver {
+    Solver *s;
+};
+
+#define API_TRY try {
+#define API_CATCH                                   \
+    }                                               \
+    catch (const CudaError &e) {                    \
+        g_last_error = e.msg;                       \
+        return 1;                                   \
+    }                                               \
+    catch (const std::exception &e) {               \
+        g_last_error = e.what();                    \
+        return 1;                                   \
+    }                                               \
+    catch (...) {                                   \
+        g_last_error = "unknown error";             \
+        return 1;                                   \
+    }
+
+extern "C" {
+
+int apm_lcl_version(void) { return APM_LCL_VERSION; }
+const char *apm_lcl_last_error(void) { return g_last_error.c_str(); }
+long long apm_lcl_last_launch_count(void) { return g_launches; }
+
+void apm_lcl_default_params(apm_lcl_params *p)
+{
+    if (!p) return;
+    std::memset(p, 0, sizeof(*p));
+    p->inlet_pressure = -1.0; p->outlet_pressure = -1.0; p->inlet_rate = -1.0; p->outlet_rate = -1.0;
+    p->density = 1.0; p->viscosity = -1.0; p->voxel_size = 1.0; p->avg_factor = 1.0; p->roughness = 0.0;
+    p->high_mask = 1e6; p->low_mask = 1e-6; p->outlet_side = APM_LCL_TOP;
+    p->rel_tol = 0.0; p->max_iter = 0; p->flags = 0;
+}
+
+int apm_lcl_solver_create(apm_lcl_solver **out, int device, int nx, int nz)
+{
+    API_TRY
+    if (!out) throw CudaError{"out pointer is NULL"};
+    *out = nullptr;
+    Solver *s = solver_new(device, nx, nz);
+    *out = new apm_lcl_solver{s};
+    g_last_error.clear();
+    return 0;
+    API_CATCH
+}
+
+int apm_lcl_solver_destroy(apm_lcl_solver *h)
+{
+    if (!h) return 0;
+    solver_free(h->s);
+    delete h;
+    return 0;
+}
+
+int apm_lcl_solver_solve(apm_lcl_solver *h, const apm_lcl_params *p, const double *aperture, apm_lcl_fields *out,
+                         apm_lcl_scalars *sc)
+{
+    API_TRY
+    if (!h || !h->s || !p) throw CudaError{"solver or params pointer is NULL"};
+    do_solve(*h->s, *p, aperture, out, sc);
+    g_last_error.clear();
+    return 0;
+    API_CATCH
+}
+
+int apm_lcl_solve(const apm_lcl_params *p, const double *aperture, int nx, int nz, int device, apm_lcl_fields *out,
+                  apm_lcl_scalars *sc)
+{
+    apm_lcl_solver *h = nullptr;
+    if (apm_lcl_solver_create(&h, device, nx, nz)) return 1;
+    const int rc = apm_lcl_solver_solve(h, p, aperture, out, sc);
+    const std::string keep = g_last_error;
+    apm_lcl_solver_destroy(h);
+    g_last_error = keep;
+    return rc;
+}
+
+int apm_lcl_conductance(const apm_lcl_params *p, const double *aperture, int nx, int nz, int device, double *width,
+                        double *trx, double *trz, apm_lcl_scalars *sc)
+{
+    Solver *s = nullptr;
+    API_TRY
+    if (!p) throw CudaError{"params pointer is NULL"};
+    validate(*p);
+    s = solver_new(device, nx, nz);
+    g_launches = 0;
+    const double *ap_dev = stage_aperture(*s, aperture);
+    launch_conductance(*s, *p, ap_dev);
+    apm_lcl_scalars local{};
+    if (!sc) sc = &local;
+    std::memset(sc, 0, sizeof(*sc));
+    double *dtrx = nullptr, *dtrz = nullptr;
+    const size_t ntrx = (size_t)nz * (nx + 1), ntrz = (size_t)(nz + 1) * nx;
+    if (trx) dtrx = is_device_ptr(trx) ? trx : (alloc_d(&dtrx, ntrx), dtrx);
+    if (trz) dtrz = is_device_ptr(trz) ? trz : (alloc_d(&dtrz, ntrz), dtrz);
+    if (trx || trz) export_reference_layout(*s, dtrx, dtrz);
+    copy_out(*s, width, s->width, s->n);
+    if (trx && dtrx != trx) copy_out(*s, trx, dtrx, ntrx);
+    if (trz && dtrz != trz) copy_out(*s, trz, dtrz, ntrz);
+    read_map_scalars(*s, *p, sc);
+    if (trx && dtrx != trx) cudaFree(dtrx);
+    if (trz && dtrz != trz) cudaFree(dtrz);
+    solver_free(s);
+    g_last_error.clear();
+    return 0;
+    }
+    catch (const CudaError &e) {
+        g_last_error = e.msg;
+        if (s) solver_free(s);
+        return 1;
+    }
+    catch (...) {
+        g_last_error = "unknown error";
+        if (s) solver_free(s);
+        return 1;
+    }
+}
+
+int apm_lcl_solver_device_field(apm_lcl_solver *h, const char *name, double **ptr, size_t *count)
+{
+    API_TRY
+    if (!h || !h->s || !name || !ptr) throw CudaError{"NULL argument"};
+    Solver &s = *h->s;
+    const std::string n(name);
+    double *p = nullptr;
+    size_t c = s.n;
+    if (n == "pressure") p = s.x;
+    else if (n == "width") p = s.width;
+    else if (n == "tx") p = s.tx;
+    else if (n == "tz") p = s.tz;
+    else if (n == "txl") { p = s.txl; c = s.nz; }
+    else if (n == "tzb") { p = s.tzb; c = s.nx; }
+    else throw CudaError{"unknown field name"};
+    *ptr = p;
+    if (count) *count = c;
+    return 0;
+    API_CATCH
+}
+
+int apm_lcl_solver_time_kernel(apm_lcl_solver *h, const char *name, int reps, double *ms, double *bytes)
+{
+    API_TRY
+    if (!h || !h->s || !name || !ms) throw CudaError{"NULL argument"};
+    Solver &s = *h->s;
+    if (!s.have_solution) throw CudaError{"time_kernel needs a completed solve (conductances and hierarchy)"};
+    CUDA_CHECK(cudaSetDevice(s.device));
+    const std::string n(name);
+    if (reps < 1) reps = 1;
+    // neutral PCG scalars so no kernel early-exits; the solver's vectors are scratch from here on
+    PcgState st{};
+    st.rz = 1.0; st.alpha = 1e-3; st.beta = 1e-3; st.bb = 1.0; st.bs = 1.0; st.tol2 = 0.0;
+    auto reset = [&]() { CUDA_CHECK(cudaMemcpyAsync(s.state, &st, sizeof st, cudaMemcpyHostToDevice, s.stream)); };
+    auto one = [&]() -> double {
+        double b = bench_launch_pcg(s, n);
+        if (b < 0) b = bench_launch_cycle(s, n);
+        if (b < 0 && n == "conductance") { launch_conductance(s, s.last_params, s.ap); b = 32.0 * (double)s.n; }
+        if (b < 0 && n == "flux") {
+            FluxOut fo{s.r, s.d, s.q, s.z, nullptr};
+            launch_flux(s, s.last_params, s.x, BoundaryValues{0, 0, 0, 0}, fo);
+            b = 64.0 * (double)s.n;
+        }
+        if (b < 0) throw CudaError{"unknown kernel name"};
+        return b;
+    };
+    reset();
+    double b = 0;
+    for (int k = 0; k < 3; k++) b = one();
+    CUDA_CHECK(cudaEventRecord(s.ev[0], s.stream));
+    for (int k = 0; k < reps; k++) one();
+    CUDA_CHECK(cudaEventRecord(s.ev[1], s.stream));
+    CUDA_CHECK(cudaStreamSynchronize(s.stream));
+    float t = 0;
+    CUDA_CHECK(cudaEventElapsedTime(&t, s.ev[0], s.ev[1]));
+    *ms = (double)t / reps;
+    if (bytes) *bytes = b;
+    s.have_solution = false;   // x, r, d, q, z were used as scratch
+    return 0;
+    API_CATCH
+}
+
+}   // extern "C"

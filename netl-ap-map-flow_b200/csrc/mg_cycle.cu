@@ -1,0 +1,394 @@
+// mg_cycle.cu -- one symmetric multigrid V-cycle, z = M^-1 r, the preconditioner of the PCG solve
+// that replaces the reference's direct D4 elimination (D4_SOLVER_MODULE.F:444-617).
+//
+// Fine level: red/black Gauss-Seidel on the matrix-free 5-point operator (faces tx/tz).
+// Coarse levels: four-colour Gauss-Seidel on the stored symmetric 9-point Galerkin operators.
+// Pre-smoothing runs the colours forward, post-smoothing backward, so M is symmetric (CG needs it).
+// Algorithmic bytes per fine cell and launch (f64): colour pass 40 B, residual 40 B, restriction
+// 8+2 B, prolongation 8+8+2 B (DESIGN.md lists the fused variants that replace these).
+#include "device_utils.cuh"
+
+namespace lcl {
+
+enum { GS_PLAIN = 0, GS_FIRST = 1, GS_LAST = 2 };
+
+__device__ __forceinline__ bool stopped(const PcgState *st) { return st && (st->converged | st->failed); }
+
+// ---------------------------------------------------------------------------------- fine level
+// One colour of red/black Gauss-Seidel.  MODE FIRST: zero initial guess (other colour := 0) and the
+// norms ||b||^2, b^T D^-1 b of the right-hand side (= PCG residual) ride along.  MODE LAST: b.x rides
+// along (= r.z of PCG).
+template <int MODE>
+__global__ void __launch_bounds__(kBlock)
+k_gs5(Fine5 v, const double *__restrict__ b, double *__restrict__ x, int color, PcgState *st, int init,
+      double *partials, unsigned int *counter)
+{
+    if (stopped(st)) return;
+    const F5 A{v};
+    const int nz = v.nz, nx = v.nx;
+    const Tiles tiles(nz, nx);
+    double acc[2] = {0.0, 0.0};
+    for (long long t = blockIdx.x; t < tiles.ntiles; t += gridDim.x) {
+        int z, xx;
+        tiles.cell(t, z, xx);
+        if (z >= nz || xx >= nx) continue;
+        const size_t i = (size_t)z * nx + xx;
+        const bool mine = ((z + xx) & 1) == color;
+        if (MODE == GS_PLAIN && !mine) continue;
+        const double bi = b[i];
+        if (MODE == GS_FIRST) {
+            const double dg = A.diag(z, xx);
+            acc[0] += bi * bi;
+            acc[1] += bi * bi / dg;
+            x[i] = mine ? bi / dg : 0.0;
+            continue;
+        }
+        double xi;
+        if (mine) {
+            const double tl = A.left(z, xx), tr = A.right(z, xx), td = A.down(z, xx), tu = A.up(z, xx);
+            double s = bi;
+            if (xx > 0) s += tl * x[i - 1];
+            if (xx + 1 < nx) s += tr * x[i + 1];
+            if (z > 0) s += td * x[i - nx];
+            if (z + 1 < nz) s += tu * x[i + nx];
+            xi = s / ((tl + tr) + (td + tu));
+            x[i] = xi;
+        } else {
+            xi = x[i];
+        }
+        if (MODE == GS_LAST) acc[0] += bi * xi;
+    }
+    if (MODE == GS_FIRST) {
+        grid_sum_finalize<2>(acc, partials, counter, [=](const double(&tot)[2]) {
+            st->rr = tot[0];
+            st->rs = tot[1];
+            if (init) {
+                st->bb = tot[0];
+                st->bs = tot[1];
+            } else if (tot[0] <= st->tol2 * st->bb && tot[1] <= st->tol2 * st->bs) {
+                st->converged = 1;
+            }
+            if (!(tot[0] == tot[0]) || !(tot[1] == tot[1])) st->failed = 1;
+        });
+    }
+    if (MODE == GS_LAST) {
+        grid_sum_finalize<2>(acc, partials, counter, [=](const double(&tot)[2]) {
+            st->rz_new = tot[0];
+            st->beta = init ? 0.0 : tot[0] / st->rz;
+            st->rz = tot[0];
+        });
+    }
+}
+
+__global__ void __launch_bounds__(kBlock)
+k_residual5(Fine5 v, const double *__restrict__ b, const double *__restrict__ x, double *__restrict__ r,
+            const PcgState *st)
+{
+    if (stopped(st)) return;
+    const F5 A{v};
+    const int nz = v.nz, nx = v.nx;
+    const Tiles tiles(nz, nx);
+    for (long long t = blockIdx.x; t < tiles.ntiles; t += gridDim.x) {
+        int z, xx;
+        tiles.cell(t, z, xx);
+        if (z >= nz || xx >= nx) continue;
+        const size_t i = (size_t)z * nx + xx;
+        const double tl = A.left(z, xx), tr = A.right(z, xx), td = A.down(z, xx), tu = A.up(z, xx);
+        const double xi = x[i];
+        double s = b[i] - ((tl + tr) + (td + tu)) * xi;
+        if (xx > 0) s += tl * x[i - 1];
+        if (xx + 1 < nx) s += tr * x[i + 1];
+        if (z > 0) s += td * x[i - nx];
+        if (z + 1 < nz) s += tu * x[i + nx];
+        r[i] = s;
+    }
+}
+
+// -------------------------------------------------------------------------------- coarse levels
+__global__ void __launch_bounds__(kBlock)
+k_gs9(Coarse9 v, const double *__restrict__ b, double *__restrict__ x, int cz, int cx, const PcgState *st)
+{
+    if (stopped(st)) return;
+    const C9 A{v};
+    const int nz = v.nz, nx = v.nx;
+    const int hz = (nz - cz + 1) / 2, hx = (nx - cx + 1) / 2;   // points of this colour
+    const Tiles tiles(hz, hx);
+    for (long long t = blockIdx.x; t < tiles.ntiles; t += gridDim.x) {
+        int a, c;
+        tiles.cell(t, a, c);
+        if (a >= hz || c >= hx) continue;
+        const int z = 2 * a + cz, xx = 2 * c + cx;
+        const size_t i = (size_t)z * nx + xx;
+        double s = b[i];
+#pragma unroll
+        for (int dz = -1; dz <= 1; dz++)
+#pragma unroll
+            for (int dx = -1; dx <= 1; dx++) {
+                if (dz == 0 && dx == 0) continue;
+                const int qz = z + dz, qx = xx + dx;
+                if (qz < 0 || qz >= nz || qx < 0 || qx >= nx) continue;
+                s += A.g(z, xx, dz, dx) * x[(size_t)qz * nx + qx];
+            }
+        x[i] = s / A.diag(z, xx);
+    }
+}
+
+__global__ void __launch_bounds__(kBlock)
+k_residual9(Coarse9 v, const double *__restrict__ b, const double *__restrict__ x, double *__restrict__ r,
+            const PcgState *st)
+{
+    if (stopped(st)) return;
+    const C9 A{v};
+    const int nz = v.nz, nx = v.nx;
+    const Tiles tiles(nz, nx);
+    for (long long t = blockIdx.x; t < tiles.ntiles; t += gridDim.x) {
+        int z, xx;
+        tiles.cell(t, z, xx);
+        if (z >= nz || xx >= nx) continue;
+        const size_t i = (size_t)z * nx + xx;
+        double s = b[i] - A.diag(z, xx) * x[i];
+#pragma unroll
+        for (int dz = -1; dz <= 1; dz++)
+#pragma unroll
+            for (int dx = -1; dx <= 1; dx++) {
+                if (dz == 0 && dx == 0) continue;
+                const int qz = z + dz, qx = xx + dx;
+                if (qz < 0 || qz >= nz || qx < 0 || qx >= nx) continue;
+                s += A.g(z, xx, dz, dx) * x[(size_t)qz * nx + qx];
+            }
+        r[i] = s;
+    }
+}
+
+// ------------------------------------------------------------------------------------ transfers
+// bc = P^T r : thread per coarse point gathers its 3x3 fine neighbourhood
+__global__ void __launch_bounds__(kBlock)
+k_restrict(Weights w, const double *__restrict__ r, int nz, int nx, double *__restrict__ bc, int nzc, int nxc,
+           const PcgState *st)
+{
+    if (stopped(st)) return;
+    const Tiles tiles(nzc, nxc);
+    for (long long t = blockIdx.x; t < tiles.ntiles; t += gridDim.x) {
+        int Z, X;
+        tiles.cell(t, Z, X);
+        if (Z >= nzc || X >= nxc) continue;
+        const int z = 2 * Z, x = 2 * X;
+        const size_t b = (size_t)Z * nxc + X;
+        const size_t i = (size_t)z * nx + x;
+        const bool xm = X > 0, xp = x + 1 < nx, zm = Z > 0, zp = z + 1 < nz;
+        double s = r[i];
+        if (xp) s += w.hw[b] * r[i + 1];
+        if (xm) s += w.he[b - 1] * r[i - 1];
+        if (zp) s += w.vs[b] * r[i + nx];
+        if (zm) s += w.vn[b - nxc] * r[i - nx];
+        if (zp && xp) s += w.csw[b] * r[i + nx + 1];
+        if (zp && xm) s += w.cse[b - 1] * r[i + nx - 1];
+        if (zm && xp) s += w.cnw[b - nxc] * r[i - nx + 1];
+        if (zm && xm) s += w.cne[b - nxc - 1] * r[i - nx - 1];
+        bc[b] = s;
+    }
+}
+
+// x += P e : thread per coarse block writes its (up to) four fine points
+__global__ void __launch_bounds__(kBlock)
+k_prolong_add(Weights w, const double *__restrict__ e, int nzc, int nxc, double *__restrict__ x, int nz, int nx,
+              const PcgState *st)
+{
+    if (stopped(st)) return;
+    const Tiles tiles(nzc, nxc);
+    for (long long t = blockIdx.x; t < tiles.ntiles; t += gridDim.x) {
+        int Z, X;
+        tiles.cell(t, Z, X);
+        if (Z >= nzc || X >= nxc) continue;
+        const int z = 2 * Z, xx = 2 * X;
+        const size_t b = (size_t)Z * nxc + X;
+        const size_t i = (size_t)z * nx + xx;
+        const bool xp = xx + 1 < nx, zp = z + 1 < nz;
+        const bool Xp = X + 1 < nxc, Zp = Z + 1 < nzc;
+        const double e00 = e[b];
+        const double e01 = Xp ? e[b + 1] : 0.0;
+        const double e10 = Zp ? e[b + nxc] : 0.0;
+        const double e11 = (Zp && Xp) ? e[b + nxc + 1] : 0.0;
+        x[i] += e00;
+        if (xp) x[i + 1] += w.hw[b] * e00 + w.he[b] * e01;
+        if (zp) x[i + nx] += w.vs[b] * e00 + w.vn[b] * e10;
+        if (zp && xp) x[i + nx + 1] += (w.csw[b] * e00 + w.cse[b] * e01) + (w.cnw[b] * e10 + w.cne[b] * e11);
+    }
+}
+
+// x = S inv S b on the coarsest level (one CTA)
+__global__ void k_coarse_solve(const double *__restrict__ inv, const double *__restrict__ scale,
+                               const double *__restrict__ b, double *__restrict__ x, int n, const PcgState *st)
+{
+    if (stopped(st)) return;
+    LCL_DYNAMIC_SMEM(double, sb);
+    for (int i = threadIdx.x; i < n; i += blockDim.x) sb[i] = scale[i] * b[i];
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        double s = 0.0;
+        for (int j = 0; j < n; j++) s += inv[(size_t)i * n + j] * sb[j];
+        x[i] = scale[i] * s;
+    }
+}
+
+__global__ void k_copy(const double *__restrict__ a, double *__restrict__ b, size_t n, const PcgState *st)
+{
+    if (stopped(st)) return;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) b[i] = a[i];
+}
+
+// fine-level b.x when the hierarchy has a single (dense) level
+__global__ void __launch_bounds__(kBlock)
+k_dot_norms(const double *__restrict__ b, const double *__restrict__ x, Fine5 v, PcgState *st, int init,
+            double *partials, unsigned int *counter)
+{
+    if (stopped(st)) return;
+    const F5 A{v};
+    const size_t n = (size_t)v.nz * v.nx;
+    double acc[3] = {0.0, 0.0, 0.0};
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const int z = (int)(i / v.nx), xx = (int)(i % v.nx);
+        const double bi = b[i];
+        acc[0] += bi * bi;
+        acc[1] += bi * bi / A.diag(z, xx);
+        acc[2] += bi * x[i];
+    }
+    grid_sum_finalize<3>(acc, partials, counter, [=](const double(&tot)[3]) {
+        st->rr = tot[0];
+        st->rs = tot[1];
+        if (init) { st->bb = tot[0]; st->bs = tot[1]; }
+        // the dense "preconditioner" is an exact solve: the next residual test decides
+        st->rz_new = tot[2];
+        st->beta = init ? 0.0 : tot[2] / st->rz;
+        st->rz = tot[2];
+        if (!init && tot[0] <= st->tol2 * st->bb && tot[1] <= st->tol2 * st->bs) st->converged = 1;
+    });
+}
+
+// ------------------------------------------------------------------------------------- driver
+double bench_launch_cycle(Solver &s, const std::string &name)
+{
+    const Fine5 v5 = s.view5();
+    const int g0 = grid_for(s, s.nz, s.nx, 8);
+    double *part = s.red + 16 * kMaxPartials;
+    unsigned int *cnt = s.red_counters + 4;
+    const double n = (double)s.n;
+    if (name == "gs5_first") {
+        LAUNCH((k_gs5<GS_FIRST>), g0, kBlock, 0, s.stream, v5, (const double *)s.r, s.z, 0, s.state, 0, part, cnt);
+        return 32.0 * n;   // b, tx, tz in; x out
+    }
+    if (name == "gs5_color") {
+        LAUNCH((k_gs5<GS_PLAIN>), g0, kBlock, 0, s.stream, v5, (const double *)s.r, s.z, 1, s.state, 0, part, cnt);
+        return 40.0 * n;   // b, x, tx, tz in; x out (whole lines move although one colour is updated)
+    }
+    if (name == "gs5_last") {
+        LAUNCH((k_gs5<GS_LAST>), g0, kBlock, 0, s.stream, v5, (const double *)s.r, s.z, 0, s.state, 0,
+               part + 4 * kMaxPartials, cnt + 1);
+        return 40.0 * n;
+    }
+    if (name == "residual5") {
+        LAUNCH(k_residual5, g0, kBlock, 0, s.stream, v5, (const double *)s.r, (const double *)s.z, s.q, s.state);
+        return 40.0 * n;
+    }
+    if (s.levels.size() > 1 && s.levels[0].w.hw) {
+        Level &c = s.levels[1];
+        if (name == "restrict0") {
+            LAUNCH(k_restrict, grid_for(s, c.nz, c.nx, 8), kBlock, 0, s.stream, s.levels[0].w, (const double *)s.q,
+                   s.nz, s.nx, c.b, c.nz, c.nx, s.state);
+            return 8.0 * n + (8.0 + 64.0) * (double)c.n;   // r in; 8 weights in, coarse rhs out
+        }
+        if (name == "prolong0") {
+            LAUNCH(k_prolong_add, grid_for(s, c.nz, c.nx, 8), kBlock, 0, s.stream, s.levels[0].w, (const double *)c.x,
+                   c.nz, c.nx, s.z, s.nz, s.nx, s.state);
+            return 16.0 * n + (8.0 + 64.0) * (double)c.n;
+        }
+    }
+    if (name == "vcycle") {
+        mg_vcycle(s, s.r, s.z, s.state, false);
+        return 0.0;
+    }
+    return -1.0;
+}
+
+static const int kColorZ[4] = {0, 0, 1, 1}, kColorX[4] = {0, 1, 0, 1};
+
+static void smooth9(Solver &s, Level &l, bool forward, int sweeps, PcgState *st)
+{
+    const Coarse9 v = l.view9();
+    for (int k = 0; k < sweeps; k++)
+        for (int c = 0; c < 4; c++) {
+            const int col = forward ? c : 3 - c;
+            const int cz = kColorZ[col], cx = kColorX[col];
+            const int hz = (l.nz - cz + 1) / 2, hx = (l.nx - cx + 1) / 2;
+            if (hz <= 0 || hx <= 0) continue;
+            LAUNCH(k_gs9, grid_for(s, hz, hx, 8), kBlock, 0, s.stream, v, l.b, l.x, cz, cx, st);
+        }
+}
+
+void mg_vcycle(Solver &s, const double *r, double *z, PcgState *st, bool init_flag)
+{
+    const int init = init_flag ? 1 : 0;
+    const Fine5 v5 = s.view5();
+    const int g0 = grid_for(s, s.nz, s.nx, 8);
+    double *part = s.red + 16 * kMaxPartials;   // slots 16.. belong to the cycle
+    unsigned int *cnt = s.red_counters + 4;
+    const size_t nlev = s.levels.size();
+
+    if (s.levels[0].w.hw == nullptr) {   // map small enough for the dense solve alone
+        Level &c = s.levels[1];
+        LAUNCH(k_coarse_solve, 1, 64, c.n * sizeof(double), s.stream, s.coarse_inv, s.coarse_scale, r, z, (int)c.n, st);
+        LAUNCH(k_dot_norms, 1, kBlock, 0, s.stream, r, z, v5, st, init, part, cnt);
+        return;
+    }
+
+    // ---- down leg, fine level
+    LAUNCH((k_gs5<GS_FIRST>), g0, kBlock, 0, s.stream, v5, r, z, 0, st, init, part, cnt);
+    LAUNCH((k_gs5<GS_PLAIN>), g0, kBlock, 0, s.stream, v5, r, z, 1, st, init, part, cnt);
+    for (int k = 1; k < s.nu_fine; k++) {
+        LAUNCH((k_gs5<GS_PLAIN>), g0, kBlock, 0, s.stream, v5, r, z, 0, st, init, part, cnt);
+        LAUNCH((k_gs5<GS_PLAIN>), g0, kBlock, 0, s.stream, v5, r, z, 1, st, init, part, cnt);
+    }
+    LAUNCH(k_residual5, g0, kBlock, 0, s.stream, v5, r, (const double *)z, s.q, st);
+    {
+        Level &c = s.levels[1];
+        LAUNCH(k_restrict, grid_for(s, c.nz, c.nx, 8), kBlock, 0, s.stream, s.levels[0].w, (const double *)s.q,
+               s.nz, s.nx, c.b, c.nz, c.nx, st);
+    }
+    // ---- down leg, coarse levels
+    for (size_t l = 1; l + 1 < nlev; l++) {
+        Level &f = s.levels[l], &c = s.levels[l + 1];
+        CUDA_CHECK(cudaMemsetAsync(f.x, 0, f.n * sizeof(double), s.stream));
+        smooth9(s, f, true, s.nu_coarse, st);
+        LAUNCH(k_residual9, grid_for(s, f.nz, f.nx, 8), kBlock, 0, s.stream, f.view9(), (const double *)f.b,
+               (const double *)f.x, f.r, st);
+        LAUNCH(k_restrict, grid_for(s, c.nz, c.nx, 8), kBlock, 0, s.stream, f.w, (const double *)f.r, f.nz, f.nx,
+               c.b, c.nz, c.nx, st);
+    }
+    // ---- coarsest: dense solve
+    {
+        Level &c = s.levels[nlev - 1];
+        LAUNCH(k_coarse_solve, 1, 64, c.n * sizeof(double), s.stream, s.coarse_inv, s.coarse_scale,
+               (const double *)c.b, c.x, (int)c.n, st);
+    }
+    // ---- up leg, coarse levels
+    for (size_t l = nlev - 2; l >= 1; l--) {
+        Level &f = s.levels[l], &c = s.levels[l + 1];
+        LAUNCH(k_prolong_add, grid_for(s, c.nz, c.nx, 8), kBlock, 0, s.stream, f.w, (const double *)c.x, c.nz, c.nx,
+               f.x, f.nz, f.nx, st);
+        smooth9(s, f, false, s.nu_coarse, st);
+    }
+    // ---- up leg, fine level
+    {
+        Level &c = s.levels[1];
+        LAUNCH(k_prolong_add, grid_for(s, c.nz, c.nx, 8), kBlock, 0, s.stream, s.levels[0].w, (const double *)c.x,
+               c.nz, c.nx, z, s.nz, s.nx, st);
+    }
+    for (int k = 1; k < s.nu_fine; k++) {
+        LAUNCH((k_gs5<GS_PLAIN>), g0, kBlock, 0, s.stream, v5, r, z, 1, st, init, part, cnt);
+        LAUNCH((k_gs5<GS_PLAIN>), g0, kBlock, 0, s.stream, v5, r, z, 0, st, init, part, cnt);
+    }
+    LAUNCH((k_gs5<GS_PLAIN>), g0, kBlock, 0, s.stream, v5, r, z, 1, st, init, part, cnt);
+    LAUNCH((k_gs5<GS_LAST>), g0, kBlock, 0, s.stream, v5, r, z, 0, st, init, part + 4 * kMaxPartials, cnt + 1);
+}
+
+}   // namespace lcl

@@ -1,0 +1,281 @@
+// mg_setup.cu -- builds the multigrid hierarchy for one set of face conductances.
+//
+// New work (the reference solves the system directly, D4_SOLVER_MODULE.F:444-617): a geometric
+// hierarchy on the same NZ x NX cell grid with operator-dependent ("black box") interpolation and
+// Galerkin coarse operators, so that 1e16+ conductance contrast (LOW-MASK contact cells,
+// APERTURE_MAP_FLOW.F:478-479) does not stall the cycle.  tools/proto_boxmg.py is the numpy
+// prototype these kernels restate on the device.
+//
+//   coarse points      = fine points with even (z,x);  nzc = (nz+1)/2, nxc = (nx+1)/2
+//   h-edge  (2Z,2X+1)  : w = (column sums of the stencil) / (diag - g_N - g_S)
+//   v-edge  (2Z+1,2X)  : w = (row sums of the stencil)    / (diag - g_E - g_W)
+//   centre  (2Z+1,2X+1): w = (g_corner + g_vert * w_hedge + g_horz * w_vedge) / diag
+//   A_c = P^T A P      : 9-point, stored symmetrically (C,E,N,NE,NW)
+#include "device_utils.cuh"
+
+namespace lcl {
+
+// ------------------------------------------------------------------------------ edge weights
+template <class Op>
+__global__ void __launch_bounds__(kBlock)
+k_weights_edges(Op A, int nzc, int nxc, Weights w)
+{
+    const int nz = A.nz(), nx = A.nx();
+    const Tiles tiles(nzc, nxc);
+    for (long long t = blockIdx.x; t < tiles.ntiles; t += gridDim.x) {
+        int Z, X;
+        tiles.cell(t, Z, X);
+        if (Z >= nzc || X >= nxc) continue;
+        const size_t b = (size_t)Z * nxc + X;
+        double hw = 0.0, he = 0.0, vs = 0.0, vn = 0.0;
+        {   // h-edge point (2Z, 2X+1)
+            const int z = 2 * Z, x = 2 * X + 1;
+            if (x < nx) {
+                const double den = A.diag(z, x) - A.g(z, x, 1, 0) - A.g(z, x, -1, 0);
+                if (den > 0.0) {
+                    hw = (A.g(z, x, 0, -1) + A.g(z, x, -1, -1) + A.g(z, x, 1, -1)) / den;
+                    if (x + 1 < nx) he = (A.g(z, x, 0, 1) + A.g(z, x, -1, 1) + A.g(z, x, 1, 1)) / den;
+                }
+            }
+        }
+        {   // v-edge point (2Z+1, 2X)
+            const int z = 2 * Z + 1, x = 2 * X;
+            if (z < nz) {
+                const double den = A.diag(z, x) - A.g(z, x, 0, 1) - A.g(z, x, 0, -1);
+                if (den > 0.0) {
+                    vs = (A.g(z, x, -1, 0) + A.g(z, x, -1, -1) + A.g(z, x, -1, 1)) / den;
+                    if (z + 1 < nz) vn = (A.g(z, x, 1, 0) + A.g(z, x, 1, -1) + A.g(z, x, 1, 1)) / den;
+                }
+            }
+        }
+        w.hw[b] = hw; w.he[b] = he; w.vs[b] = vs; w.vn[b] = vn;
+    }
+}
+
+// ---------------------------------------------------------------------------- centre weights
+template <class Op>
+__global__ void __launch_bounds__(kBlock)
+k_weights_centres(Op A, int nzc, int nxc, Weights w)
+{
+    const int nz = A.nz(), nx = A.nx();
+    const Tiles tiles(nzc, nxc);
+    for (long long t = blockIdx.x; t < tiles.ntiles; t += gridDim.x) {
+        int Z, X;
+        tiles.cell(t, Z, X);
+        if (Z >= nzc || X >= nxc) continue;
+        const size_t b = (size_t)Z * nxc + X;
+        double c[4] = {0.0, 0.0, 0.0, 0.0};   // sw, se, nw, ne
+        const int z = 2 * Z + 1, x = 2 * X + 1;
+        if (z < nz && x < nx) {
+            const double dg = A.diag(z, x);
+            if (dg > 0.0) {
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    const int cz = (k & 2) ? 1 : -1, cx = (k & 1) ? 1 : -1;
+                    // corner coarse point exists?
+                    if (z + cz >= nz || x + cx >= nx) continue;
+                    double acc = A.g(z, x, cz, cx);
+                    // via the h-edge point (z+cz, x): block row (cz<0 ? Z : Z+1), block col X
+                    {
+                        const size_t hb = (size_t)(cz < 0 ? Z : Z + 1) * nxc + X;
+                        acc += A.g(z, x, cz, 0) * (cx < 0 ? w.hw[hb] : w.he[hb]);
+                    }
+                    // via the v-edge point (z, x+cx): block row Z, block col (cx<0 ? X : X+1)
+                    {
+                        const size_t vb = (size_t)Z * nxc + (cx < 0 ? X : X + 1);
+                        acc += A.g(z, x, 0, cx) * (cz < 0 ? w.vs[vb] : w.vn[vb]);
+                    }
+                    c[k] = acc / dg;
+                }
+            }
+        }
+        w.csw[b] = c[0]; w.cse[b] = c[1]; w.cnw[b] = c[2]; w.cne[b] = c[3];
+    }
+}
+
+// ------------------------------------------------------------------------------ Galerkin RAP
+// thread per coarse point I: A_c(I,J) = sum_p sum_q P(p,I) A(p,q) P(q,J) for J in {I,E,N,NE,NW}
+template <class Op>
+__global__ void __launch_bounds__(kBlock)
+k_galerkin(Op A, int nzc, int nxc, Weights w, double *__restrict__ Cc, double *__restrict__ Ec,
+           double *__restrict__ Nc, double *__restrict__ NEc, double *__restrict__ NWc)
+{
+    const int nz = A.nz(), nx = A.nx();
+    const Tiles tiles(nzc, nxc);
+    for (long long t = blockIdx.x; t < tiles.ntiles; t += gridDim.x) {
+        int Z, X;
+        tiles.cell(t, Z, X);
+        if (Z >= nzc || X >= nxc) continue;
+        double acc[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+        const int Jz[5] = {Z, Z, Z + 1, Z + 1, Z + 1};
+        const int Jx[5] = {X, X + 1, X, X + 1, X - 1};
+        for (int pz = 2 * Z - 1; pz <= 2 * Z + 1; pz++) {
+            if (pz < 0 || pz >= nz) continue;
+            for (int px = 2 * X - 1; px <= 2 * X + 1; px++) {
+                if (px < 0 || px >= nx) continue;
+                const double wI = pweight(w, nzc, nxc, pz, px, Z, X);
+                if (wI == 0.0) continue;
+#pragma unroll
+                for (int dz = -1; dz <= 1; dz++) {
+                    const int qz = pz + dz;
+                    if (qz < 0 || qz >= nz) continue;
+#pragma unroll
+                    for (int dx = -1; dx <= 1; dx++) {
+                        const int qx = px + dx;
+                        if (qx < 0 || qx >= nx) continue;
+                        const double a = (dz == 0 && dx == 0) ? A.diag(pz, px) : -A.g(pz, px, dz, dx);
+                        if (a == 0.0) continue;
+                        const double wa = wI * a;
+#pragma unroll
+                        for (int j = 0; j < 5; j++) acc[j] += wa * pweight(w, nzc, nxc, qz, qx, Jz[j], Jx[j]);
+                    }
+                }
+            }
+        }
+        const size_t i = (size_t)Z * nxc + X;
+        Cc[i] = acc[0];
+        Ec[i] = (X + 1 < nxc) ? -acc[1] : 0.0;
+        Nc[i] = (Z + 1 < nzc) ? -acc[2] : 0.0;
+        NEc[i] = (Z + 1 < nzc && X + 1 < nxc) ? -acc[3] : 0.0;
+        NWc[i] = (Z + 1 < nzc && X > 0) ? -acc[4] : 0.0;
+    }
+}
+
+// ------------------------------------------------------------------------ coarsest: dense inverse
+// One CTA.  Builds S A S (S = diag^-1/2) densely in global memory and inverts it by Gauss-Jordan
+// without pivoting (SPD).  inv is [n][n]; the cycle applies x = S inv S b.
+__global__ void k_coarse_inverse(Coarse9 v, double *__restrict__ inv, double *__restrict__ scale, int n)
+{
+    const C9 A{v};
+    const int nx = v.nx, nz = v.nz;
+    LCL_DYNAMIC_SMEM(double, sh);   // aug[n][2n]
+    double *aug = sh;
+    const int tid = threadIdx.x, nt = blockDim.x;
+    for (int i = tid; i < n; i += nt) scale[i] = rsqrt(A.diag(i / nx, i % nx));
+    __syncthreads();
+    for (int e = tid; e < n * 2 * n; e += nt) aug[e] = 0.0;
+    __syncthreads();
+    for (int i = tid; i < n; i += nt) {
+        const int z = i / nx, x = i % nx;
+        aug[i * 2 * n + i] = 1.0;   // scaled diagonal
+        for (int dz = -1; dz <= 1; dz++)
+            for (int dx = -1; dx <= 1; dx++) {
+                if (dz == 0 && dx == 0) continue;
+                const int qz = z + dz, qx = x + dx;
+                if (qz < 0 || qz >= nz || qx < 0 || qx >= nx) continue;
+                const int j = qz * nx + qx;
+                aug[i * 2 * n + j] = -A.g(z, x, dz, dx) * scale[i] * scale[j];
+            }
+        aug[i * 2 * n + n + i] = 1.0;
+    }
+    __syncthreads();
+    for (int k = 0; k < n; k++) {
+        const double piv = aug[k * 2 * n + k];
+        __syncthreads();
+        for (int j = tid; j < 2 * n; j += nt) aug[k * 2 * n + j] /= piv;
+        __syncthreads();
+        for (int e = tid; e < n * 2 * n; e += nt) {
+            const int i = e / (2 * n), j = e % (2 * n);
+            if (i == k) continue;
+            const double f = aug[i * 2 * n + k];
+            if (f != 0.0 && j != k) aug[e] -= f * aug[k * 2 * n + j];
+        }
+        __syncthreads();
+        for (int i = tid; i < n; i += nt)
+            if (i != k) aug[i * 2 * n + k] = 0.0;
+        __syncthreads();
+    }
+    for (int e = tid; e < n * n; e += nt) inv[e] = aug[(e / n) * 2 * n + n + (e % n)];
+}
+
+// ------------------------------------------------------------------------------------ host side
+constexpr int kCoarsestCells = 48;   // dense inverse in shared memory: 48*96*8 = 36 KB
+
+static void alloc_d(double **p, size_t count) { CUDA_CHECK(cudaMalloc((void **)p, (count ? count : 1) * sizeof(double))); }
+
+void mg_allocate(Solver &s)
+{
+    s.levels.clear();
+    Level l0;
+    l0.nz = s.nz; l0.nx = s.nx; l0.n = s.n;
+    s.levels.push_back(l0);
+    while ((long long)s.levels.back().nz * s.levels.back().nx > kCoarsestCells) {
+        Level &f = s.levels.back();
+        Level c;
+        c.nz = (f.nz + 1) / 2; c.nx = (f.nx + 1) / 2; c.n = (size_t)c.nz * c.nx;
+        double **wp[8] = {&f.w.hw, &f.w.he, &f.w.vs, &f.w.vn, &f.w.csw, &f.w.cse, &f.w.cnw, &f.w.cne};
+        for (auto p : wp) alloc_d(p, c.n);
+        double **cp[8] = {&c.C, &c.E, &c.N, &c.NE, &c.NW, &c.x, &c.b, &c.r};
+        for (auto p : cp) alloc_d(p, c.n);
+        s.levels.push_back(c);
+    }
+    if (s.levels.size() == 1) {
+        // tiny map: still give it one coarse "level" equal to itself?  No: the cycle handles a
+        // single-level hierarchy by smoothing + dense solve of a 9-point copy of the fine operator.
+        Level c;
+        c.nz = s.nz; c.nx = s.nx; c.n = s.n;
+        double **cp[8] = {&c.C, &c.E, &c.N, &c.NE, &c.NW, &c.x, &c.b, &c.r};
+        for (auto p : cp) alloc_d(p, c.n);
+        s.levels.push_back(c);
+        s.levels[0].w = Weights{};   // marks "identity transfer"
+    }
+    s.coarse_n = (int)s.levels.back().n;
+    alloc_d(&s.coarse_inv, (size_t)s.coarse_n * s.coarse_n);
+    alloc_d(&s.coarse_scale, s.coarse_n);
+}
+
+void mg_free(Solver &s)
+{
+    for (auto &l : s.levels) {
+        double *ptrs[16] = {l.C, l.E, l.N, l.NE, l.NW, l.x, l.b, l.r, l.w.hw, l.w.he, l.w.vs, l.w.vn,
+                            l.w.csw, l.w.cse, l.w.cnw, l.w.cne};
+        for (double *p : ptrs)
+            if (p) cudaFree(p);
+    }
+    s.levels.clear();
+    if (s.coarse_inv) cudaFree(s.coarse_inv);
+    if (s.coarse_scale) cudaFree(s.coarse_scale);
+    s.coarse_inv = s.coarse_scale = nullptr;
+}
+
+// copy of the fine 5-point operator as a 9-point one (only for maps with <= kCoarsestCells cells)
+__global__ void k_fine_as_coarse(Fine5 v, double *C, double *E, double *N, double *NE, double *NW)
+{
+    const F5 A{v};
+    const int n = v.nz * v.nx;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const int z = i / v.nx, x = i % v.nx;
+        C[i] = A.diag(z, x);
+        E[i] = A.g(z, x, 0, 1);
+        N[i] = A.g(z, x, 1, 0);
+        NE[i] = 0.0;
+        NW[i] = 0.0;
+    }
+}
+
+template <class Op>
+static void build_next(Solver &s, const Op &A, Level &f, Level &c)
+{
+    const int grid = grid_for(s, c.nz, c.nx, 8);
+    LAUNCH((k_weights_edges<Op>), grid, kBlock, 0, s.stream, A, c.nz, c.nx, f.w);
+    LAUNCH((k_weights_centres<Op>), grid, kBlock, 0, s.stream, A, c.nz, c.nx, f.w);
+    LAUNCH((k_galerkin<Op>), grid, kBlock, 0, s.stream, A, c.nz, c.nx, f.w, c.C, c.E, c.N, c.NE, c.NW);
+}
+
+void mg_setup(Solver &s)
+{
+    if (s.levels[0].w.hw == nullptr) {
+        Level &c = s.levels[1];
+        LAUNCH(k_fine_as_coarse, 1, 64, 0, s.stream, s.view5(), c.C, c.E, c.N, c.NE, c.NW);
+    } else {
+        build_next(s, F5{s.view5()}, s.levels[0], s.levels[1]);
+        for (size_t l = 1; l + 1 < s.levels.size(); l++)
+            build_next(s, C9{s.levels[l].view9()}, s.levels[l], s.levels[l + 1]);
+    }
+    const Level &last = s.levels.back();
+    const int n = (int)last.n;
+    const size_t smem = (size_t)n * 2 * n * sizeof(double);
+    LAUNCH(k_coarse_inverse, 1, 256, smem, s.stream, last.view9(), s.coarse_inv, s.coarse_scale, n);
+}
+
+}   // namespace lcl

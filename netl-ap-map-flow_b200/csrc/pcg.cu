@@ -1,0 +1,236 @@
+// pcg.cu -- matrix-free preconditioned conjugate gradients for the LCL pressure system.
+//
+// The system is the one SOLVER assembles (APERTURE_MAP_FLOW.F:628-650) with the Dirichlet rows of
+// ADD_DIRICHLET_BOUND_COND (D4_SOLVER_MODULE.F:170-257) folded in:  sum_f T_f (p_i - p_nbr) = 0 per
+// cell, boundary faces contributing T_b p_i on the diagonal and T_b P_b on the right-hand side.
+// TT/CC are never materialised: every kernel reads the face conductances tx/tz directly.
+// Algorithmic bytes per cell (f64): spmv 32 (d, tx, tz in; q out), update 48 (x, d, r, q in; x, r
+// out), direction 24 (z, d in; d out).  All scalars (alpha, beta, norms, convergence flag) stay on
+// the device; the host polls one small struct.
+#include "device_utils.cuh"
+
+namespace lcl {
+
+__device__ __forceinline__ bool stopped(const PcgState *st) { return st->converged | st->failed; }
+
+// r = b (x0 = 0), x = 0
+__global__ void __launch_bounds__(kBlock)
+k_init_rhs(Fine5 v, BoundaryValues bv, double *__restrict__ r, double *__restrict__ x)
+{
+    const int nz = v.nz, nx = v.nx;
+    const Tiles tiles(nz, nx);
+    for (long long t = blockIdx.x; t < tiles.ntiles; t += gridDim.x) {
+        int z, xx;
+        tiles.cell(t, z, xx);
+        if (z >= nz || xx >= nx) continue;
+        const size_t i = (size_t)z * nx + xx;
+        double b = 0.0;
+        if (xx == 0) b += v.txl[z] * bv.left;
+        if (xx == nx - 1) b += v.tx[i] * bv.right;
+        if (z == 0) b += v.tzb[xx] * bv.bottom;
+        if (z == nz - 1) b += v.tz[i] * bv.top;
+        r[i] = b;
+        x[i] = 0.0;
+    }
+}
+
+// q = A d and d.q;  alpha = rz / d.q
+__global__ void __launch_bounds__(kBlock)
+k_spmv5(Fine5 v, const double *__restrict__ d, double *__restrict__ q, PcgState *st, double *partials,
+        unsigned int *counter)
+{
+    if (stopped(st)) return;
+    const F5 A{v};
+    const int nz = v.nz, nx = v.nx;
+    const Tiles tiles(nz, nx);
+    double acc[1] = {0.0};
+    for (long long t = blockIdx.x; t < tiles.ntiles; t += gridDim.x) {
+        int z, xx;
+        tiles.cell(t, z, xx);
+        if (z >= nz || xx >= nx) continue;
+        const size_t i = (size_t)z * nx + xx;
+        const double tl = A.left(z, xx), tr = A.right(z, xx), td = A.down(z, xx), tu = A.up(z, xx);
+        const double di = d[i];
+        double s = ((tl + tr) + (td + tu)) * di;
+        if (xx > 0) s -= tl * d[i - 1];
+        if (xx + 1 < nx) s -= tr * d[i + 1];
+        if (z > 0) s -= td * d[i - nx];
+        if (z + 1 < nz) s -= tu * d[i + nx];
+        q[i] = s;
+        acc[0] += di * s;
+    }
+    grid_sum_finalize<1>(acc, partials, counter, [=](const double(&tot)[1]) {
+        st->dq = tot[0];
+        if (!(tot[0] > 0.0) || !(st->rz == st->rz)) {
+            st->failed = 1;
+            st->alpha = 0.0;
+        } else {
+            st->alpha = st->rz / tot[0];
+        }
+        st->iter += 1;
+    });
+}
+
+// x += alpha d ; r -= alpha q
+__global__ void __launch_bounds__(256)
+k_update(double *__restrict__ x, double *__restrict__ r, const double *__restrict__ d, const double *__restrict__ q,
+         size_t n, const PcgState *st)
+{
+    if (stopped(st)) return;
+    const double alpha = st->alpha;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        x[i] += alpha * d[i];
+        r[i] -= alpha * q[i];
+    }
+}
+
+// d = z + beta d
+__global__ void __launch_bounds__(256)
+k_direction(double *__restrict__ d, const double *__restrict__ z, size_t n, const PcgState *st, int init)
+{
+    if (stopped(st)) return;
+    const double beta = st->beta;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        d[i] = init ? z[i] : z[i] + beta * d[i];
+}
+
+// true residual r = b - A x with both norms (verification after the recurrence says "converged")
+__global__ void __launch_bounds__(kBlock)
+k_true_residual(Fine5 v, BoundaryValues bv, const double *__restrict__ x, double *__restrict__ r, double *out,
+                double *partials, unsigned int *counter)
+{
+    const F5 A{v};
+    const int nz = v.nz, nx = v.nx;
+    const Tiles tiles(nz, nx);
+    double acc[2] = {0.0, 0.0};
+    for (long long t = blockIdx.x; t < tiles.ntiles; t += gridDim.x) {
+        int z, xx;
+        tiles.cell(t, z, xx);
+        if (z >= nz || xx >= nx) continue;
+        const size_t i = (size_t)z * nx + xx;
+        const double tl = A.left(z, xx), tr = A.right(z, xx), td = A.down(z, xx), tu = A.up(z, xx);
+        const double dg = (tl + tr) + (td + tu);
+        double s = -dg * x[i];
+        s += tl * (xx > 0 ? x[i - 1] : bv.left);
+        s += tr * (xx + 1 < nx ? x[i + 1] : bv.right);
+        s += td * (z > 0 ? x[i - nx] : bv.bottom);
+        s += tu * (z + 1 < nz ? x[i + nx] : bv.top);
+        r[i] = s;
+        acc[0] += s * s;
+        acc[1] += s * s / dg;
+    }
+    grid_sum_finalize<2>(acc, partials, counter, [=](const double(&tot)[2]) {
+        out[0] = tot[0];
+        out[1] = tot[1];
+    });
+}
+
+double bench_launch_pcg(Solver &s, const std::string &name)
+{
+    const Fine5 v5 = s.view5();
+    const int g0 = grid_for(s, s.nz, s.nx, 8), g1 = s.num_sms * 8;
+    const double n = (double)s.n;
+    if (name == "spmv") {
+        LAUNCH(k_spmv5, g0, kBlock, 0, s.stream, v5, (const double *)s.d, s.q, s.state, s.red, s.red_counters);
+        return 32.0 * n;
+    }
+    if (name == "update") {
+        LAUNCH(k_update, g1, 256, 0, s.stream, s.x, s.r, (const double *)s.d, (const double *)s.q, s.n,
+               (const PcgState *)s.state);
+        return 48.0 * n;
+    }
+    if (name == "direction") {
+        LAUNCH(k_direction, g1, 256, 0, s.stream, s.d, (const double *)s.z, s.n, (const PcgState *)s.state, 0);
+        return 24.0 * n;
+    }
+    return -1.0;
+}
+
+static void poll_state(Solver &s)
+{
+    CUDA_CHECK(cudaMemcpyAsync(s.state_host, s.state, sizeof(PcgState), cudaMemcpyDeviceToHost, s.stream));
+    CUDA_CHECK(cudaStreamSynchronize(s.stream));
+}
+
+int pcg_solve(Solver &s, const BoundaryValues &bv, double rel_tol, int max_iter, apm_lcl_scalars *sc)
+{
+    const Fine5 v5 = s.view5();
+    const int g0 = grid_for(s, s.nz, s.nx, 8);
+    const int g1 = s.num_sms * 8;
+    double *part = s.red;                 // slots 0..15 belong to pcg.cu / conductance / flux
+    unsigned int *cnt = s.red_counters;
+    const size_t n = s.n;
+    // cells per poll: small maps are launch bound, so look at the flag less often
+    const int check_every = n >= (size_t)4 << 20 ? 1 : (n >= (size_t)1 << 18 ? 2 : 4);
+
+    PcgState h{};
+    h.tol2 = rel_tol * rel_tol;
+    CUDA_CHECK(cudaMemcpyAsync(s.state, &h, sizeof h, cudaMemcpyHostToDevice, s.stream));
+    LAUNCH(k_init_rhs, g0, kBlock, 0, s.stream, v5, bv, s.r, s.x);
+    mg_vcycle(s, s.r, s.z, s.state, true);
+    LAUNCH(k_direction, g1, 256, 0, s.stream, s.d, (const double *)s.z, n, (const PcgState *)s.state, 1);
+
+    int iters = 0, restarts = 0;
+    bool done = false;
+    double true_rr = 0.0, true_rs = 0.0, bb = 0.0, bs = 0.0;
+    poll_state(s);
+    bb = s.state_host->bb; bs = s.state_host->bs;
+    if (!(bb > 0.0)) {   // zero right-hand side: x = 0 is the solution
+        if (sc) { sc->iterations += 0; sc->converged = 1; sc->rel_residual = 0.0; sc->rel_residual_scaled = 0.0; }
+        return 0;
+    }
+    while (!done) {
+        while (iters < max_iter) {
+            for (int k = 0; k < check_every && iters < max_iter; k++, iters++) {
+                LAUNCH(k_spmv5, g0, kBlock, 0, s.stream, v5, (const double *)s.d, s.q, s.state, part, cnt);
+                LAUNCH(k_update, g1, 256, 0, s.stream, s.x, s.r, (const double *)s.d, (const double *)s.q, n,
+                       (const PcgState *)s.state);
+                mg_vcycle(s, s.r, s.z, s.state, false);
+                LAUNCH(k_direction, g1, 256, 0, s.stream, s.d, (const double *)s.z, n, (const PcgState *)s.state, 0);
+            }
+            poll_state(s);
+            if (s.state_host->converged || s.state_host->failed) break;
+        }
+        const int dev_iters = s.state_host->iter;
+        // verify on the true residual (the recurrence can drift under 1e16 contrast)
+        LAUNCH(k_true_residual, g0, kBlock, 0, s.stream, v5, bv, (const double *)s.x, s.q, s.scal + 12,
+               part + 8 * kMaxPartials, cnt + 2);
+        CUDA_CHECK(cudaMemcpyAsync(s.scal_host + 12, s.scal + 12, 2 * sizeof(double), cudaMemcpyDeviceToHost, s.stream));
+        CUDA_CHECK(cudaStreamSynchronize(s.stream));
+        true_rr = s.scal_host[12]; true_rs = s.scal_host[13];
+        const bool ok = true_rr <= h.tol2 * bb && true_rs <= h.tol2 * bs;
+        iters = dev_iters;
+        if (ok || s.state_host->failed || iters >= max_iter || restarts >= 3) {
+            done = true;
+            if (sc) {
+                sc->iterations += iters;
+                sc->converged = ok ? 1 : 0;
+                sc->rel_residual = sqrt(true_rr / bb);
+                sc->rel_residual_scaled = sqrt(true_rs / bs);
+            }
+            if (s.state_host->failed && !ok) {
+                g_last_error = "PCG breakdown (non-positive curvature or non-finite residual)";
+                return -1;
+            }
+        } else {
+            // restart from the true residual: r := b - A x, z = M^-1 r, d = z
+            restarts++;
+            CUDA_CHECK(cudaMemcpyAsync(s.r, s.q, n * sizeof(double), cudaMemcpyDeviceToDevice, s.stream));
+            PcgState h2 = *s.state_host;
+            h2.converged = 0; h2.failed = 0;
+            CUDA_CHECK(cudaMemcpyAsync(s.state, &h2, sizeof h2, cudaMemcpyHostToDevice, s.stream));
+            CUDA_CHECK(cudaStreamSynchronize(s.stream));
+            mg_vcycle(s, s.r, s.z, s.state, false);
+            // after this cycle beta = rz_new/rz_old is meaningless: force a steepest-descent restart
+            LAUNCH(k_direction, g1, 256, 0, s.stream, s.d, (const double *)s.z, n, (const PcgState *)s.state, 1);
+            poll_state(s);
+            if (s.state_host->converged) {
+                // the cycle's own test passed on the true residual it was given
+                continue;
+            }
+        }
+    }
+    return iters;
+}
+
+}   // namespace lcl

@@ -1,0 +1,159 @@
+"""GPU parity tests proper (-m gpu): libapmlcl.so through its C ABI vs the CPU oracle, the
+reference's golden files, and size-independent properties at BASELINE.json's full sizes.
+
+Tolerances (north_star): masks / counters / cell indexing bit exact; pressure within 1e-6 of
+max|p|; flow rate within 1e-6 relative.  Face conductances are compared at 1e-9 relative because
+CUDA's atan/tan differ from glibc's in the last ulp and tan(theta)-theta cancels.
+"""
+import numpy as np
+import pytest
+
+from helpers import load_csv, load_map, synth_aperture
+from oracle import oracle_binding as ob
+from apmapflow_b200 import lcl
+from apmapflow_b200._lib import Params, LEFT, RIGHT, TOP, BOTTOM
+
+pytestmark = pytest.mark.gpu
+
+
+def params(**kw):
+    base = dict(inlet_pressure=100.0, outlet_pressure=0.0, density=1000.0, viscosity=1.0,
+                voxel_size=20.0e-6, avg_factor=10.0, roughness=0.0, high_mask=100.0, low_mask=1e-4,
+                outlet_side=TOP)
+    base.update(kw)
+    return Params.defaults(**base)
+
+
+def synth_params(**kw):
+    # SURVEY.md 8d common .inp values
+    base = dict(inlet_pressure=1000.0, outlet_pressure=0.0, density=1000.0, viscosity=1.0e-3,
+                voxel_size=10.0e-6, avg_factor=1.0, roughness=0.0, high_mask=100.0, low_mask=1e-4,
+                outlet_side=TOP)
+    base.update(kw)
+    return Params.defaults(**base)
+
+
+def check_against_oracle(p, a, ptol=1e-6, qtol=1e-6):
+    o, so = ob.solve(p, a)
+    w, trx, trz, sc = lcl.conductance(p, a)
+    assert np.array_equal(w, o["width"])                                  # clamp masks: bit exact
+    assert np.array_equal(trx == 0, o["trx"] == 0) and np.array_equal(trz == 0, o["trz"] == 0)
+    assert np.allclose(trx, o["trx"], rtol=1e-9, atol=0) and np.allclose(trz, o["trz"], rtol=1e-9, atol=0)
+    assert (sc["zeros"], sc["masked"]) == (so["zeros"], so["masked"])     # counters: bit exact
+    assert sc["min_aper"] == so["min_aper"] and sc["max_aper"] == so["max_aper"]
+    assert sc["raw_aper"] == pytest.approx(so["raw_aper"], rel=1e-12)
+    assert sc["avg_aper"] == pytest.approx(so["avg_aper"], rel=1e-12)
+    f, s = lcl.lcl_solve(p, a)
+    assert s["gpu_launches"] > 0 and s["converged"] == 1
+    scale = np.abs(o["pressure"]).max()
+    assert np.abs(f["pressure"] - o["pressure"]).max() / scale < ptol
+    assert s["flow"] == pytest.approx(so["flow"], rel=qtol)
+    assert s["inlet_pressure"] == pytest.approx(so["inlet_pressure"], rel=1e-6, abs=1e-9)
+    assert s["outlet_pressure"] == pytest.approx(so["outlet_pressure"], rel=1e-6, abs=1e-9)
+    qscale = np.abs(o["flow_m"]).max()
+    for k in ("flow_x", "flow_z", "flow_m"):
+        assert np.abs(f[k] - o[k]).max() <= 1e-5 * qscale
+    assert np.abs(f["reynolds"] - o["reynolds"]).max() <= 1e-5 * np.abs(o["reynolds"]).max()
+    assert np.array_equal(f["aperture"], o["width"])
+    r = f["residual"]
+    assert np.nanmax(r) == 1.0 and np.nanmin(r) >= 0.0
+    return f, s, o, so
+
+
+def test_golden_parallel_plate_matches_reference_files():
+    """BASELINE config 1: coverage_test.inp on ParallelPlate-1vox.txt vs the reference's own outputs."""
+    a = load_map("ParallelPlate-1vox.txt")
+    p = params(voxel_size=10e-6)
+    f, s = lcl.lcl_solve(p, a)
+    assert np.abs(f["pressure"] - load_csv("coverage_test_pres-orig.csv.gz")).max() <= 1e-6 * 100.0
+    assert np.allclose(f["flow_z"], load_csv("coverage_test_flow-z-orig.csv.gz"), rtol=1e-6, atol=0)
+    assert np.allclose(f["flow_m"], load_csv("coverage_test_flow-m-orig.csv.gz"), rtol=1e-6, atol=0)
+    assert np.allclose(f["aperture"], load_csv("coverage_test_aper-orig.csv.gz"), rtol=1e-7, atol=0)
+    assert np.abs(f["flow_x"]).max() < 1e-6 * np.abs(f["flow_z"]).max()
+    assert s["outlet_rate"] == pytest.approx(0.833333333333e-14, rel=1e-6)      # coverage_test_stats-orig.yaml
+    assert (s["zeros"], s["masked"]) == (0, 0)
+
+
+@pytest.mark.parametrize("name", ["Fracture1ApertureMap-10avg.txt", "Fracture3ApertureMap-10avg.txt"])
+@pytest.mark.parametrize("side", [LEFT, RIGHT, TOP, BOTTOM])
+def test_fixture_maps_all_outlet_sides(name, side):
+    check_against_oracle(params(outlet_side=side), load_map(name))
+
+
+def test_roughness_and_high_mask():
+    check_against_oracle(params(roughness=0.25, high_mask=6.0), load_map("Fracture3ApertureMap-10avg.txt"), ptol=5e-6)
+
+
+@pytest.mark.parametrize("side", [LEFT, TOP])
+@pytest.mark.parametrize("mode", ["inlet_rate", "outlet_rate"])
+def test_rate_boundary_conditions(side, mode):
+    a = load_map("Fracture3ApertureMap-10avg.txt")
+    if mode == "inlet_rate":
+        p = params(outlet_side=side, inlet_pressure=-1.0, outlet_pressure=50.0, inlet_rate=1e-9)
+    else:
+        p = params(outlet_side=side, inlet_pressure=500.0, outlet_pressure=-1.0, outlet_rate=1e-9)
+    f, s, o, so = check_against_oracle(p, a)
+    assert s["outlet_rate"] == pytest.approx(1e-9, rel=1e-6)
+
+
+@pytest.mark.parametrize("shape", [(1, 1), (1, 7), (6, 1), (2, 2), (5, 9), (7, 7), (16, 3), (33, 65), (100, 37)])
+def test_tiny_ragged_and_degenerate_maps(shape):
+    a = synth_aperture(shape[0], shape[1], seed=shape[0] * 31 + shape[1], sigma_c=0)
+    check_against_oracle(synth_params(), a)
+
+
+@pytest.mark.parametrize("n,contact", [(256, 0.0), (256, 0.2), (384, 0.2)])
+def test_synthetic_lognormal_maps_vs_oracle(n, contact):
+    """BASELINE configs 2/3 recipe at sizes the direct D4 oracle finishes in seconds."""
+    a = synth_aperture(n, n, seed=n, sigma_c=8, contact=contact, sigma_k=16)
+    f, s, o, so = check_against_oracle(synth_params(), a)
+    if contact:
+        assert so["zeros"] > 0.15 * n * n
+
+
+def test_invalid_inputs_fail_with_reference_messages():
+    a = synth_aperture(8, 8, seed=1, sigma_c=0)
+    with pytest.raises(lcl._lib.LclError, match="INVALID BOUNDARY"):
+        lcl.lcl_solve(params(inlet_rate=1e-9), a)
+    with pytest.raises(lcl._lib.LclError, match="INVAILD VISCOSITY"):
+        lcl.lcl_solve(params(viscosity=-1.0), a)
+
+
+def _inflow_outflow(f, p_in, p_out, trz):
+    q_in = (trz[0, :] * (p_in - f["pressure"][0, :])).sum()
+    q_out = (trz[-1, :] * (f["pressure"][-1, :] - p_out)).sum()
+    return q_in, q_out
+
+
+@pytest.mark.parametrize("n,contact", [(2048, 0.0), (2048, 0.2)])
+def test_full_size_properties_2048(n, contact):
+    """BASELINE config 2 at full size: no oracle possible in seconds, so size-independent checks:
+    mass balance, maximum principle, self-convergence under a 1000x tighter tolerance, determinism."""
+    a = synth_aperture(n, n, seed=7, sigma_c=8, contact=contact, sigma_k=16)
+    p = synth_params()
+    with lcl.LclSolver(n, n) as solver:
+        f, s = solver.solve(p, a, fields=("pressure", "flow_z"))
+        f_again, _ = solver.solve(p, a, fields=("pressure",))
+        assert np.array_equal(f["pressure"], f_again["pressure"])          # deterministic reductions
+        p.rel_tol = 1e-13
+        g, s2 = solver.solve(p, a, fields=("pressure",))
+    assert s["converged"] == 1 and s["rel_residual"] <= 1e-10 and s["rel_residual_scaled"] <= 1e-10
+    assert np.abs(f["pressure"] - g["pressure"]).max() / 1000.0 < 1e-6
+    assert f["pressure"].min() >= -1e-6 and f["pressure"].max() <= 1000.0 + 1e-6
+    _, _, trz, _ = lcl.conductance(synth_params(), a)
+    q_in, q_out = _inflow_outflow(f, 1000.0, 0.0, trz)
+    assert q_in == pytest.approx(q_out, rel=1e-7)
+    assert abs(s["flow"]) == pytest.approx(q_out, rel=1e-6)
+    assert s["iterations"] < 60
+
+
+def test_torch_cuda_tensor_io_matches_host_io():
+    import torch
+    a = synth_aperture(300, 200, seed=11, sigma_c=4, contact=0.1, sigma_k=8)
+    p = synth_params()
+    f_host, s_host = lcl.lcl_solve(p, a)
+    f_dev, s_dev = lcl.lcl_solve(p, torch.from_numpy(a).cuda())
+    for k in lcl.FIELD_NAMES:
+        assert f_dev[k].is_cuda
+        assert np.array_equal(f_dev[k].cpu().numpy(), f_host[k], equal_nan=True)
+    assert s_dev["flow"] == s_host["flow"]

@@ -1,0 +1,91 @@
+"""Pre-GPU debugging aid: the kernel SOURCES of libapmlcl compiled for the CPU with the emulation
+shim in tests/sim/ (fibers for CUDA threads) and compared with the oracle.  This checks indexing,
+boundary handling and the PCG/multigrid control flow without a GPU; it says nothing about the
+product binary -- the GPU parity tests (tests/test_gpu_parity.py, -m gpu) do that through
+libapmlcl.so.  The sim library is never loaded by the product package.
+"""
+import numpy as np
+import pytest
+
+from helpers import load_map, synth_aperture
+from oracle import oracle_binding as ob
+from apmapflow_b200 import lcl
+from apmapflow_b200._lib import Params, LEFT, RIGHT, TOP, BOTTOM
+from sim import sim_lib
+
+
+@pytest.fixture(scope="module")
+def sim():
+    return sim_lib.load()
+
+
+def params(**kw):
+    base = dict(inlet_pressure=100.0, outlet_pressure=0.0, density=1000.0, viscosity=1.0,
+                voxel_size=20.0e-6, avg_factor=10.0, roughness=0.0, high_mask=100.0, low_mask=1e-4,
+                outlet_side=TOP)
+    base.update(kw)
+    return Params.defaults(**base)
+
+
+def check(sim, p, a, ptol=1e-6, qtol=1e-6):
+    o, so = ob.solve(p, a)
+    w, trx, trz, sc = lcl.conductance(p, a, lib=sim)
+    assert np.array_equal(w, o["width"])
+    assert np.array_equal(trx == 0, o["trx"] == 0) and np.array_equal(trz == 0, o["trz"] == 0)
+    assert np.allclose(trx, o["trx"], rtol=1e-9, atol=0) and np.allclose(trz, o["trz"], rtol=1e-9, atol=0)
+    assert (sc["zeros"], sc["masked"]) == (so["zeros"], so["masked"])
+    f, s = lcl.lcl_solve(p, a, lib=sim)
+    scale = np.abs(o["pressure"]).max()
+    assert np.abs(f["pressure"] - o["pressure"]).max() / scale < ptol
+    assert s["flow"] == pytest.approx(so["flow"], rel=qtol)
+    assert s["inlet_pressure"] == pytest.approx(so["inlet_pressure"], rel=1e-6, abs=1e-9)
+    assert s["outlet_pressure"] == pytest.approx(so["outlet_pressure"], rel=1e-6, abs=1e-9)
+    qscale = np.abs(o["flow_m"]).max()      # a component can be pure rounding noise (1-row maps)
+    for k in ("flow_x", "flow_z", "flow_m"):
+        assert np.abs(f[k] - o[k]).max() <= 1e-5 * qscale
+    assert np.abs(f["reynolds"] - o["reynolds"]).max() <= 1e-5 * np.abs(o["reynolds"]).max()
+    assert np.array_equal(f["aperture"], o["width"])
+    assert s["converged"] == 1
+    return f, s, o, so
+
+
+@pytest.mark.parametrize("side", [LEFT, RIGHT, TOP, BOTTOM])
+def test_sim_all_sides_odd_sizes(sim, side):
+    a = load_map("Fracture1ApertureMap-10avg.txt")[20:73, 40:101]     # 53 x 61, has zero cells
+    check(sim, params(outlet_side=side), a)
+
+
+def test_sim_roughness_and_high_mask(sim):
+    a = load_map("Fracture3ApertureMap-10avg.txt")[:48, :64]
+    check(sim, params(roughness=0.25, high_mask=6.0), a, ptol=5e-6)
+
+
+@pytest.mark.parametrize("mode", ["inlet_rate", "outlet_rate"])
+def test_sim_rate_bc(sim, mode):
+    a = load_map("Fracture3ApertureMap-10avg.txt")[30:70, 10:58]
+    if mode == "inlet_rate":
+        p = params(outlet_side=RIGHT, inlet_pressure=-1.0, outlet_pressure=50.0, inlet_rate=1e-9)
+    else:
+        p = params(outlet_side=BOTTOM, inlet_pressure=500.0, outlet_pressure=-1.0, outlet_rate=1e-9)
+    f, s, o, so = check(sim, p, a)
+    assert s["outlet_rate"] == pytest.approx(1e-9, rel=1e-6)
+
+
+@pytest.mark.parametrize("shape", [(1, 1), (1, 7), (6, 1), (2, 2), (5, 9), (7, 7), (16, 3)])
+def test_sim_tiny_and_degenerate_maps(sim, shape):
+    a = synth_aperture(shape[0], shape[1], seed=shape[0] * 31 + shape[1], sigma_c=0)
+    check(sim, params(voxel_size=1e-5, avg_factor=1.0, viscosity=1e-3, inlet_pressure=1000.0), a)
+
+
+def test_sim_synthetic_contact_map(sim):
+    a = synth_aperture(64, 80, seed=5, contact=0.2, sigma_k=5)
+    f, s, o, so = check(sim, params(voxel_size=1e-5, avg_factor=1.0, viscosity=1e-3, inlet_pressure=1000.0), a)
+    assert so["zeros"] > 0
+
+
+def test_sim_invalid_boundary_conditions_fail(sim):
+    a = synth_aperture(8, 8, seed=1, sigma_c=0)
+    with pytest.raises(lcl._lib.LclError):
+        lcl.lcl_solve(params(inlet_rate=1e-9), a, lib=sim)          # both pressures and a rate
+    with pytest.raises(lcl._lib.LclError):
+        lcl.lcl_solve(params(viscosity=-1.0), a, lib=sim)

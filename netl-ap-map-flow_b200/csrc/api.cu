@@ -415,7 +415,7 @@ int apm_lcl_solver_time_kernel(apm_lcl_solver *h, const char *name, int reps, do
     if (reps < 1) reps = 1;
     // neutral PCG scalars so no kernel early-exits; the solver's vectors are scratch from here on
     PcgState st{};
-    st.rz = 1.0; st.alpha = 1e-3; st.beta = 1e-3; st.bb = 1.0; st.bs = 1.0; st.tol2 = 0.0;
+    st.rz = 1.0; st.alpha = 1e-3; st.beta = 1e-3; st.bb = 1.0; st.bs = 1.0; st.tol2 = 0.0; st.dx = st.dx_prev = st.dx_prev2 = 1e300;
     auto reset = [&]() { CUDA_CHECK(cudaMemcpyAsync(s.state, &st, sizeof st, cudaMemcpyHostToDevice, s.stream)); };
     auto one = [&]() -> double {
         double b = bench_launch_pcg(s, n);

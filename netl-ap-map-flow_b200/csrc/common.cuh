@@ -97,10 +97,12 @@ struct PcgState {
     double rr, rs;      // ||r||^2 and r^T D^-1 r of the latest residual
     double bb, bs;      // same for the right-hand side
     double tol2;        // rel_tol^2
-    int converged;      // set on device when both tests pass
+    double dx, dx_prev, dx_prev2; // max |alpha d_i| of the last three updates (pointwise change of the iterate)
+    double dx_tol;      // both must be <= dx_tol (absolute, = 2.5e-7 * pressure scale) before stopping
+    int res_ok;         // number of iterations at which both residual-norm tests have passed
+    int converged;      // set on device when all tests pass
     int failed;         // non-finite / non-positive curvature
     int iter;
-    int pad;
 };
 
 constexpr int kMaxPartials = 4096;   // per-reduction partial slots (>= any grid we launch)

@@ -139,6 +139,42 @@ __device__ __forceinline__ void grid_sum_finalize(double (&v)[NV], double *parti
     }
 }
 
+// same pattern for a maximum (values >= 0)
+template <class Fin>
+__device__ __forceinline__ void grid_max_finalize(double v, double *partials, unsigned int *counter, Fin fin)
+{
+    __shared__ double smem[32];
+    __shared__ bool is_last;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = (blockDim.x + 31) >> 5;
+    auto block_max = [&](double a) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) a = fmax(a, __shfl_xor_sync(0xffffffffu, a, o));
+        if (lane == 0) smem[warp] = a;
+        __syncthreads();
+        a = lane < nwarps ? smem[lane] : 0.0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) a = fmax(a, __shfl_xor_sync(0xffffffffu, a, o));
+        __syncthreads();
+        return a;
+    };
+    v = block_max(v);
+    const int nblocks = gridDim.x;
+    if (tid == 0) {
+        partials[blockIdx.x] = v;
+        __threadfence();
+        const unsigned int t = atomicInc(counter, (unsigned int)(nblocks - 1));
+        is_last = (t == (unsigned int)(nblocks - 1));
+    }
+    __syncthreads();
+    if (is_last) {
+        __threadfence();
+        double a = 0.0;
+        for (int i = tid; i < nblocks; i += blockDim.x) a = fmax(a, ldcg(&partials[i]));
+        a = block_max(a);
+        if (tid == 0) fin(a);
+    }
+}
+
 // tile iteration: 1-D grid, each block walks 32x8 tiles of an nz x nx grid (one cell per thread)
 struct Tiles {
     int tiles_x;

@@ -8,7 +8,7 @@ CUDA's atan/tan differ from glibc's in the last ulp and tan(theta)-theta cancels
 import numpy as np
 import pytest
 
-from helpers import load_csv, load_map, synth_aperture
+from helpers import anchored_open_mask, load_csv, load_map, synth_aperture
 from oracle import oracle_binding as ob
 from apmapflow_b200 import lcl
 from apmapflow_b200._lib import Params, LEFT, RIGHT, TOP, BOTTOM
@@ -33,7 +33,7 @@ def synth_params(**kw):
     return Params.defaults(**base)
 
 
-def check_against_oracle(p, a, ptol=1e-6, qtol=1e-6):
+def check_against_oracle(p, a, ptol=1e-6, qtol=1e-6, pmask=None):
     o, so = ob.solve(p, a)
     w, trx, trz, sc = lcl.conductance(p, a)
     assert np.array_equal(w, o["width"])                                  # clamp masks: bit exact
@@ -46,7 +46,10 @@ def check_against_oracle(p, a, ptol=1e-6, qtol=1e-6):
     f, s = lcl.lcl_solve(p, a)
     assert s["gpu_launches"] > 0 and s["converged"] == 1
     scale = np.abs(o["pressure"]).max()
-    assert np.abs(f["pressure"] - o["pressure"]).max() / scale < ptol
+    perr = np.abs(f["pressure"] - o["pressure"]) / scale
+    if pmask is not None:       # see helpers.anchored_open_mask: floating pockets are ill defined in f64
+        perr = perr[pmask]
+    assert perr.max() < ptol
     assert s["flow"] == pytest.approx(so["flow"], rel=qtol)
     assert s["inlet_pressure"] == pytest.approx(so["inlet_pressure"], rel=1e-6, abs=1e-9)
     assert s["outlet_pressure"] == pytest.approx(so["outlet_pressure"], rel=1e-6, abs=1e-9)
@@ -106,7 +109,7 @@ def test_tiny_ragged_and_degenerate_maps(shape):
 def test_synthetic_lognormal_maps_vs_oracle(n, contact):
     """BASELINE configs 2/3 recipe at sizes the direct D4 oracle finishes in seconds."""
     a = synth_aperture(n, n, seed=n, sigma_c=8, contact=contact, sigma_k=16)
-    f, s, o, so = check_against_oracle(synth_params(), a)
+    f, s, o, so = check_against_oracle(synth_params(), a, pmask=anchored_open_mask(a) if contact else None)
     if contact:
         assert so["zeros"] > 0.15 * n * n
 
@@ -135,10 +138,12 @@ def test_full_size_properties_2048(n, contact):
         f, s = solver.solve(p, a, fields=("pressure", "flow_z"))
         f_again, _ = solver.solve(p, a, fields=("pressure",))
         assert np.array_equal(f["pressure"], f_again["pressure"])          # deterministic reductions
-        p.rel_tol = 1e-13
-        g, s2 = solver.solve(p, a, fields=("pressure",))
+        p.rel_tol = 1e-12
+        g, s2 = solver.solve(p, a, fields=("pressure", "flow_z"))
     assert s["converged"] == 1 and s["rel_residual"] <= 1e-10 and s["rel_residual_scaled"] <= 1e-10
-    assert np.abs(f["pressure"] - g["pressure"]).max() / 1000.0 < 1e-6
+    main = anchored_open_mask(a)
+    assert np.abs(f["pressure"] - g["pressure"])[main].max() / 1000.0 < 1e-6
+    assert np.abs(f["flow_z"] - g["flow_z"]).max() <= 1e-6 * np.abs(g["flow_z"]).max()
     assert f["pressure"].min() >= -1e-6 and f["pressure"].max() <= 1000.0 + 1e-6
     _, _, trz, _ = lcl.conductance(synth_params(), a)
     q_in, q_out = _inflow_outflow(f, 1000.0, 0.0, trz)

@@ -7,7 +7,7 @@ libapmlcl.so.  The sim library is never loaded by the product package.
 import numpy as np
 import pytest
 
-from helpers import load_map, synth_aperture
+from helpers import anchored_open_mask, load_map, synth_aperture
 from oracle import oracle_binding as ob
 from apmapflow_b200 import lcl
 from apmapflow_b200._lib import Params, LEFT, RIGHT, TOP, BOTTOM
@@ -27,7 +27,7 @@ def params(**kw):
     return Params.defaults(**base)
 
 
-def check(sim, p, a, ptol=1e-6, qtol=1e-6):
+def check(sim, p, a, ptol=1e-6, qtol=1e-6, pmask=None):
     o, so = ob.solve(p, a)
     w, trx, trz, sc = lcl.conductance(p, a, lib=sim)
     assert np.array_equal(w, o["width"])
@@ -36,7 +36,10 @@ def check(sim, p, a, ptol=1e-6, qtol=1e-6):
     assert (sc["zeros"], sc["masked"]) == (so["zeros"], so["masked"])
     f, s = lcl.lcl_solve(p, a, lib=sim)
     scale = np.abs(o["pressure"]).max()
-    assert np.abs(f["pressure"] - o["pressure"]).max() / scale < ptol
+    perr = np.abs(f["pressure"] - o["pressure"]) / scale
+    if pmask is not None:       # see helpers.anchored_open_mask: floating pockets are ill defined in f64
+        perr = perr[pmask]
+    assert perr.max() < ptol
     assert s["flow"] == pytest.approx(so["flow"], rel=qtol)
     assert s["inlet_pressure"] == pytest.approx(so["inlet_pressure"], rel=1e-6, abs=1e-9)
     assert s["outlet_pressure"] == pytest.approx(so["outlet_pressure"], rel=1e-6, abs=1e-9)
@@ -79,7 +82,8 @@ def test_sim_tiny_and_degenerate_maps(sim, shape):
 
 def test_sim_synthetic_contact_map(sim):
     a = synth_aperture(64, 80, seed=5, contact=0.2, sigma_k=5)
-    f, s, o, so = check(sim, params(voxel_size=1e-5, avg_factor=1.0, viscosity=1e-3, inlet_pressure=1000.0), a)
+    f, s, o, so = check(sim, params(voxel_size=1e-5, avg_factor=1.0, viscosity=1e-3, inlet_pressure=1000.0), a,
+                        pmask=anchored_open_mask(a))
     assert so["zeros"] > 0
 
 

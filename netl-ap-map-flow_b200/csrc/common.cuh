@@ -59,33 +59,37 @@ inline int div_up(long long a, long long b) { return (int)((a + b - 1) / b); }
 //        tx[z][x] = right face of cell (z,x)  (x = nx-1 : right boundary face, TRX(IZ,NX))
 //        tz[z][x] = top   face of cell (z,x)  (z = nz-1 : top boundary face,   TRZ(NZ,IX))
 //        txl[z]   = left boundary face TRX(IZ,0),  tzb[x] = bottom boundary face TRZ(0,IX)
-//   level >= 1: Galerkin 9-point operators stored symmetrically as positive couplings
-//        C (diagonal), E -> (z,x+1), N -> (z+1,x), NE -> (z+1,x+1), NW -> (z+1,x-1);
-//        entries whose neighbour does not exist are stored as 0.
+//   level >= 1: Galerkin 9-point operators stored symmetrically in "difference form":
+//        couplings E -> (z,x+1), N -> (z+1,x), NE -> (z+1,x+1), NW -> (z+1,x-1) (0 if the neighbour
+//        does not exist), absorption S (what is left of the row sum: the Dirichlet boundary terms)
+//        and C = S + sum of the eight couplings.  A x is always evaluated as
+//        S x_p + sum g (x_p - x_q): a pocket of open cells behind ~1e-14-relative leak conductances
+//        keeps its leak information instead of losing it to cancellation (tools/proto_gth.py).
 struct Fine5 {
     const double *tx, *tz, *txl, *tzb;
     int nz, nx;
 };
 struct Coarse9 {
-    const double *C, *E, *N, *NE, *NW;
+    const double *C, *S, *E, *N, *NE, *NW;
     int nz, nx;
 };
 
 // interpolation weights fine(level l) <- coarse(level l+1), one entry per coarse 2x2 block
 // (Z,X): hw/he for the h-edge point (2Z,2X+1), vs/vn for the v-edge point (2Z+1,2X),
-// csw/cse/cnw/cne for the centre point (2Z+1,2X+1).
+// csw/cse/cnw/cne for the centre point (2Z+1,2X+1).  th/tv/tc = 1 - (sum of that point's weights),
+// computed without subtraction (it is exactly 0 away from Dirichlet boundaries).
 struct Weights {
-    double *hw, *he, *vs, *vn, *csw, *cse, *cnw, *cne;
+    double *hw, *he, *vs, *vn, *csw, *cse, *cnw, *cne, *th, *tv, *tc;
 };
 
 struct Level {
     int nz = 0, nx = 0;
     size_t n = 0;
     // coarse levels only
-    double *C = nullptr, *E = nullptr, *N = nullptr, *NE = nullptr, *NW = nullptr;
+    double *C = nullptr, *S = nullptr, *E = nullptr, *N = nullptr, *NE = nullptr, *NW = nullptr;
     double *x = nullptr, *b = nullptr, *r = nullptr;
     Weights w{};   // weights to the NEXT coarser level (absent on the coarsest)
-    Coarse9 view9() const { return Coarse9{C, E, N, NE, NW, nz, nx}; }
+    Coarse9 view9() const { return Coarse9{C, S, E, N, NE, NW, nz, nx}; }
 };
 
 // PCG scalars live on the device; kernels read alpha/beta from here, the host only polls.

@@ -23,6 +23,16 @@ struct F5 {
     {
         return (left(z, x) + right(z, x)) + (down(z, x) + up(z, x));
     }
+    // absorption: the Dirichlet boundary faces of this cell (0 in the interior)
+    __device__ __forceinline__ double S(int z, int x) const
+    {
+        double s = 0.0;
+        if (x == 0) s += v.txl[z];
+        if (x == v.nx - 1) s += v.tx[(size_t)z * v.nx + x];
+        if (z == 0) s += v.tzb[x];
+        if (z == v.nz - 1) s += v.tz[(size_t)z * v.nx + x];
+        return s;
+    }
     // coupling to an existing neighbour, 0 outside the grid / for the (absent) diagonal neighbours
     __device__ __forceinline__ double g(int z, int x, int dz, int dx) const
     {
@@ -45,6 +55,7 @@ struct F5 {
 struct C9 {
     Coarse9 v;
     __device__ __forceinline__ double diag(int z, int x) const { return v.C[(size_t)z * v.nx + x]; }
+    __device__ __forceinline__ double S(int z, int x) const { return v.S[(size_t)z * v.nx + x]; }
     __device__ __forceinline__ double g(int z, int x, int dz, int dx) const
     {
         const size_t i = (size_t)z * v.nx + x;
@@ -81,6 +92,14 @@ __device__ __forceinline__ double pweight(const Weights &w, int nzc, int nxc, in
     if (dx == 0) return dz == 1 ? w.vs[b] : w.vn[b];
     if (dz == 1) return dx == 1 ? w.csw[b] : w.cse[b];
     return dx == 1 ? w.cnw[b] : w.cne[b];
+}
+
+// 1 - (sum of the interpolation weights of fine point (qz,qx)); exactly 0 for coarse points
+__device__ __forceinline__ double pdeficit(const Weights &w, int nxc, int qz, int qx)
+{
+    const size_t b = (size_t)(qz >> 1) * nxc + (qx >> 1);
+    if (qz & 1) return (qx & 1) ? w.tc[b] : w.tv[b];
+    return (qx & 1) ? w.th[b] : 0.0;
 }
 
 // ---------------------------------------------------------------------------------------------

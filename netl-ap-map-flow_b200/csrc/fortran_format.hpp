@@ -1,0 +1,110 @@
+// fortran_format.hpp -- gfortran-compatible numeric edit descriptors for the drop-in output files.
+//
+// The reference writes every file with Fortran formatted I/O (G15.8 for CSV maps,
+// apmapflow/src/APERTURE_MAP_FLOW.F:905-915; G20.12 for the stat files :1184,1207; E14.6 for VTK
+// :1245, OUTPUT_MODULE.F:328; F/E/G/I in the log).  The golden test diffs those files line by line
+// (test/fortran/bin/test_model_code_coverage:115-155), so the digits, padding, "-0.0000000" and the
+// three-digit-exponent form ("0.1027-100") have to match.  Digits come from printf's correctly
+// rounded conversion, which is also what libgfortran uses internally.
+#pragma once
+
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+
+namespace ffmt {
+
+inline std::string stars(int w) { return std::string((size_t)(w > 0 ? w : 1), '*'); }
+
+inline std::string rjust(const std::string &s, int w)
+{
+    if ((int)s.size() >= w) return s;
+    return std::string((size_t)(w - (int)s.size()), ' ') + s;
+}
+
+// Fw.d
+inline std::string F(int w, int d, double x)
+{
+    if (std::isnan(x)) return rjust("NaN", w);
+    if (std::isinf(x)) return rjust(x > 0 ? "Infinity" : "-Infinity", w).size() > (size_t)w ? rjust(x > 0 ? "Inf" : "-Inf", w) : rjust(x > 0 ? "Infinity" : "-Infinity", w);
+    char buf[512];
+    snprintf(buf, sizeof buf, "%.*f", d, x);
+    std::string s(buf);
+    if ((int)s.size() > w) {   // gfortran drops the optional leading zero when the field is too narrow
+        if (s.compare(0, 2, "0.") == 0) s = s.substr(1);
+        else if (s.compare(0, 3, "-0.") == 0) s = "-" + s.substr(2);
+    }
+    if ((int)s.size() > w) return stars(w);
+    return rjust(s, w);
+}
+
+// Ew.d (scale factor 0): [-]0.ddddE+ee, exponent "+eee" without the E when it needs three digits
+inline std::string E(int w, int d, double x)
+{
+    if (std::isnan(x)) return rjust("NaN", w);
+    if (std::isinf(x)) return rjust(x > 0 ? "Infinity" : "-Infinity", w);
+    char buf[512];
+    const bool neg = std::signbit(x);
+    const double a = std::fabs(x);
+    std::string digits;
+    int ex = 0;
+    if (a == 0.0) {
+        digits.assign((size_t)d, '0');
+        ex = 0;
+    } else {
+        snprintf(buf, sizeof buf, "%.*e", d - 1, a);   // D.DDDDe+XX
+        const char *e = strchr(buf, 'e');
+        ex = atoi(e + 1) + 1;
+        for (const char *p = buf; p < e; p++)
+            if (*p != '.') digits.push_back(*p);
+    }
+    char ebuf[16];
+    if (std::abs(ex) < 100) snprintf(ebuf, sizeof ebuf, "E%c%02d", ex < 0 ? '-' : '+', std::abs(ex));
+    else snprintf(ebuf, sizeof ebuf, "%c%03d", ex < 0 ? '-' : '+', std::abs(ex));
+    std::string s = std::string(neg ? "-" : "") + "0." + digits + ebuf;
+    if ((int)s.size() > w) s = std::string(neg ? "-" : "") + "." + digits + ebuf;
+    if ((int)s.size() > w) return stars(w);
+    return rjust(s, w);
+}
+
+// Gw.d: F(w-4).(d-s) followed by four blanks when the value rounded to d digits has
+// 0 <= s <= d digits before the point (0.1 <= |x| < 10^d), otherwise Ew.d
+inline std::string G(int w, int d, double x)
+{
+    if (std::isnan(x) || std::isinf(x)) return E(w, d, x);
+    const double a = std::fabs(x);
+    if (a == 0.0) return F(w - 4, d - 1, x) + "    ";
+    char buf[64];
+    snprintf(buf, sizeof buf, "%.*e", d - 1, a);
+    const int s = atoi(strchr(buf, 'e') + 1) + 1;
+    if (s < 0 || s > d) return E(w, d, x);
+    return F(w - 4, d - s, x) + "    ";
+}
+
+// Iw.m
+inline std::string I(int w, int m, long long v)
+{
+    char buf[64];
+    snprintf(buf, sizeof buf, "%0*lld", m > 0 ? m : 1, v < 0 ? -v : v);
+    std::string s = std::string(v < 0 ? "-" : "") + buf;
+    if (w == 0) return s;
+    if ((int)s.size() > w) return stars(w);
+    return rjust(s, w);
+}
+
+// Aw for output: right justified in w columns (truncated on the right if longer)
+inline std::string A(int w, const std::string &s)
+{
+    if ((int)s.size() >= w) return s.substr(0, (size_t)w);
+    return rjust(s, w);
+}
+
+inline std::string rtrim(std::string s)
+{
+    while (!s.empty() && s.back() == ' ') s.pop_back();
+    return s;
+}
+
+}   // namespace ffmt

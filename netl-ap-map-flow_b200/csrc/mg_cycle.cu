@@ -103,11 +103,12 @@ k_residual5(Fine5 v, const double *__restrict__ b, const double *__restrict__ x,
         const size_t i = (size_t)z * nx + xx;
         const double tl = A.left(z, xx), tr = A.right(z, xx), td = A.down(z, xx), tu = A.up(z, xx);
         const double xi = x[i];
-        double s = b[i] - ((tl + tr) + (td + tu)) * xi;
-        if (xx > 0) s += tl * x[i - 1];
-        if (xx + 1 < nx) s += tr * x[i + 1];
-        if (z > 0) s += td * x[i - nx];
-        if (z + 1 < nz) s += tu * x[i + nx];
+        // difference form: boundary faces see the homogeneous Dirichlet value 0
+        double s = b[i];
+        s -= tl * (xi - (xx > 0 ? x[i - 1] : 0.0));
+        s -= tr * (xi - (xx + 1 < nx ? x[i + 1] : 0.0));
+        s -= td * (xi - (z > 0 ? x[i - nx] : 0.0));
+        s -= tu * (xi - (z + 1 < nz ? x[i + nx] : 0.0));
         r[i] = s;
     }
 }
@@ -154,7 +155,8 @@ k_residual9(Coarse9 v, const double *__restrict__ b, const double *__restrict__ 
         tiles.cell(t, z, xx);
         if (z >= nz || xx >= nx) continue;
         const size_t i = (size_t)z * nx + xx;
-        double s = b[i] - A.diag(z, xx) * x[i];
+        const double xi = x[i];
+        double s = b[i] - A.S(z, xx) * xi;
 #pragma unroll
         for (int dz = -1; dz <= 1; dz++)
 #pragma unroll
@@ -162,7 +164,7 @@ k_residual9(Coarse9 v, const double *__restrict__ b, const double *__restrict__ 
                 if (dz == 0 && dx == 0) continue;
                 const int qz = z + dz, qx = xx + dx;
                 if (qz < 0 || qz >= nz || qx < 0 || qx >= nx) continue;
-                s += A.g(z, xx, dz, dx) * x[(size_t)qz * nx + qx];
+                s -= A.g(z, xx, dz, dx) * (xi - x[(size_t)qz * nx + qx]);
             }
         r[i] = s;
     }

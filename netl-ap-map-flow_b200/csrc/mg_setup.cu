@@ -7,10 +7,15 @@
 // prototype these kernels restate on the device.
 //
 //   coarse points      = fine points with even (z,x);  nzc = (nz+1)/2, nxc = (nx+1)/2
-//   h-edge  (2Z,2X+1)  : w = (column sums of the stencil) / (diag - g_N - g_S)
-//   v-edge  (2Z+1,2X)  : w = (row sums of the stencil)    / (diag - g_E - g_W)
+//   h-edge  (2Z,2X+1)  : w = (column sums of the stencil) / (S + all couplings but g_N, g_S)
+//   v-edge  (2Z+1,2X)  : w = (row sums of the stencil)    / (S + all couplings but g_E, g_W)
 //   centre  (2Z+1,2X+1): w = (g_corner + g_vert * w_hedge + g_horz * w_vedge) / diag
-//   A_c = P^T A P      : 9-point, stored symmetrically (C,E,N,NE,NW)
+//   A_c = P^T A P      : 9-point, stored symmetrically in difference form (S, E, N, NE, NW; C = S + sum g)
+// Nothing here subtracts conductances: denominators are sums of non-negative terms, the weight
+// deficit 1 - sum(w) is propagated analytically (S/den), and the coarse absorption is
+// S_c = P^T (A s) with s = 1 - deficit, evaluated in difference form.  With a subtractive formulation
+// the leak conductance of a closed pocket (1e-14 of its internal couplings) drowns in rounding and
+// the coarse operators become indefinite (tools/proto_gth.py).
 #include "device_utils.cuh"
 
 namespace lcl {
@@ -27,28 +32,30 @@ k_weights_edges(Op A, int nzc, int nxc, Weights w)
         tiles.cell(t, Z, X);
         if (Z >= nzc || X >= nxc) continue;
         const size_t b = (size_t)Z * nxc + X;
-        double hw = 0.0, he = 0.0, vs = 0.0, vn = 0.0;
+        double hw = 0.0, he = 0.0, vs = 0.0, vn = 0.0, th = 0.0, tv = 0.0;
         {   // h-edge point (2Z, 2X+1)
             const int z = 2 * Z, x = 2 * X + 1;
             if (x < nx) {
-                const double den = A.diag(z, x) - A.g(z, x, 1, 0) - A.g(z, x, -1, 0);
-                if (den > 0.0) {
-                    hw = (A.g(z, x, 0, -1) + A.g(z, x, -1, -1) + A.g(z, x, 1, -1)) / den;
-                    if (x + 1 < nx) he = (A.g(z, x, 0, 1) + A.g(z, x, -1, 1) + A.g(z, x, 1, 1)) / den;
-                }
+                const double west = A.g(z, x, 0, -1) + A.g(z, x, -1, -1) + A.g(z, x, 1, -1);
+                const double east = (x + 1 < nx) ? A.g(z, x, 0, 1) + A.g(z, x, -1, 1) + A.g(z, x, 1, 1) : 0.0;
+                const double sp = A.S(z, x);
+                const double den = (west + east) + sp;
+                if (den > 0.0) { hw = west / den; he = east / den; th = sp / den; }
+                else th = 1.0;
             }
         }
         {   // v-edge point (2Z+1, 2X)
             const int z = 2 * Z + 1, x = 2 * X;
             if (z < nz) {
-                const double den = A.diag(z, x) - A.g(z, x, 0, 1) - A.g(z, x, 0, -1);
-                if (den > 0.0) {
-                    vs = (A.g(z, x, -1, 0) + A.g(z, x, -1, -1) + A.g(z, x, -1, 1)) / den;
-                    if (z + 1 < nz) vn = (A.g(z, x, 1, 0) + A.g(z, x, 1, -1) + A.g(z, x, 1, 1)) / den;
-                }
+                const double south = A.g(z, x, -1, 0) + A.g(z, x, -1, -1) + A.g(z, x, -1, 1);
+                const double north = (z + 1 < nz) ? A.g(z, x, 1, 0) + A.g(z, x, 1, -1) + A.g(z, x, 1, 1) : 0.0;
+                const double sp = A.S(z, x);
+                const double den = (south + north) + sp;
+                if (den > 0.0) { vs = south / den; vn = north / den; tv = sp / den; }
+                else tv = 1.0;
             }
         }
-        w.hw[b] = hw; w.he[b] = he; w.vs[b] = vs; w.vn[b] = vn;
+        w.hw[b] = hw; w.he[b] = he; w.vs[b] = vs; w.vn[b] = vn; w.th[b] = th; w.tv[b] = tv;
     }
 }
 
@@ -65,39 +72,52 @@ k_weights_centres(Op A, int nzc, int nxc, Weights w)
         if (Z >= nzc || X >= nxc) continue;
         const size_t b = (size_t)Z * nxc + X;
         double c[4] = {0.0, 0.0, 0.0, 0.0};   // sw, se, nw, ne
+        double tc = 0.0;
         const int z = 2 * Z + 1, x = 2 * X + 1;
         if (z < nz && x < nx) {
             const double dg = A.diag(z, x);
             if (dg > 0.0) {
+                // deficit: own absorption + what the four edge neighbours already lack
+                double def = A.S(z, x);
+                def += A.g(z, x, -1, 0) * w.th[(size_t)Z * nxc + X];
+                if (z + 1 < nz) def += A.g(z, x, 1, 0) * w.th[(size_t)(Z + 1) * nxc + X];
+                def += A.g(z, x, 0, -1) * w.tv[(size_t)Z * nxc + X];
+                if (x + 1 < nx) def += A.g(z, x, 0, 1) * w.tv[(size_t)Z * nxc + X + 1];
+                tc = def / dg;
 #pragma unroll
                 for (int k = 0; k < 4; k++) {
                     const int cz = (k & 2) ? 1 : -1, cx = (k & 1) ? 1 : -1;
-                    // corner coarse point exists?
-                    if (z + cz >= nz || x + cx >= nx) continue;
+                    if (z + cz >= nz || x + cx >= nx) {
+                        // the corner coarse point does not exist: what would have gone there is lost
+                        // to the deficit only through the edge neighbours' own (zero) weights
+                        continue;
+                    }
                     double acc = A.g(z, x, cz, cx);
-                    // via the h-edge point (z+cz, x): block row (cz<0 ? Z : Z+1), block col X
-                    {
+                    {   // via the h-edge point (z+cz, x): block row (cz<0 ? Z : Z+1), block col X
                         const size_t hb = (size_t)(cz < 0 ? Z : Z + 1) * nxc + X;
                         acc += A.g(z, x, cz, 0) * (cx < 0 ? w.hw[hb] : w.he[hb]);
                     }
-                    // via the v-edge point (z, x+cx): block row Z, block col (cx<0 ? X : X+1)
-                    {
+                    {   // via the v-edge point (z, x+cx): block row Z, block col (cx<0 ? X : X+1)
                         const size_t vb = (size_t)Z * nxc + (cx < 0 ? X : X + 1);
                         acc += A.g(z, x, 0, cx) * (cz < 0 ? w.vs[vb] : w.vn[vb]);
                     }
                     c[k] = acc / dg;
                 }
+            } else {
+                tc = 1.0;
             }
         }
-        w.csw[b] = c[0]; w.cse[b] = c[1]; w.cnw[b] = c[2]; w.cne[b] = c[3];
+        w.csw[b] = c[0]; w.cse[b] = c[1]; w.cnw[b] = c[2]; w.cne[b] = c[3]; w.tc[b] = tc;
     }
 }
 
 // ------------------------------------------------------------------------------ Galerkin RAP
-// thread per coarse point I: A_c(I,J) = sum_p sum_q P(p,I) A(p,q) P(q,J) for J in {I,E,N,NE,NW}
+// thread per coarse point I: couplings -A_c(I,J) = -sum_p sum_q P(p,I) A(p,q) P(q,J) for J in
+// {E,N,NE,NW}, and the absorption S_c(I) = sum_p P(p,I) (A s)_p with s = 1 - deficit in difference
+// form, (A s)_p = S_p s_p + sum_q g_pq (t_q - t_p).  The diagonal follows in k_coarse_diag.
 template <class Op>
 __global__ void __launch_bounds__(kBlock)
-k_galerkin(Op A, int nzc, int nxc, Weights w, double *__restrict__ Cc, double *__restrict__ Ec,
+k_galerkin(Op A, int nzc, int nxc, Weights w, double *__restrict__ Sc, double *__restrict__ Ec,
            double *__restrict__ Nc, double *__restrict__ NEc, double *__restrict__ NWc)
 {
     const int nz = A.nz(), nx = A.nx();
@@ -106,15 +126,18 @@ k_galerkin(Op A, int nzc, int nxc, Weights w, double *__restrict__ Cc, double *_
         int Z, X;
         tiles.cell(t, Z, X);
         if (Z >= nzc || X >= nxc) continue;
-        double acc[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
-        const int Jz[5] = {Z, Z, Z + 1, Z + 1, Z + 1};
-        const int Jx[5] = {X, X + 1, X, X + 1, X - 1};
+        double acc[4] = {0.0, 0.0, 0.0, 0.0};
+        double sabs = 0.0;
+        const int Jz[4] = {Z, Z + 1, Z + 1, Z + 1};
+        const int Jx[4] = {X + 1, X, X + 1, X - 1};
         for (int pz = 2 * Z - 1; pz <= 2 * Z + 1; pz++) {
             if (pz < 0 || pz >= nz) continue;
             for (int px = 2 * X - 1; px <= 2 * X + 1; px++) {
                 if (px < 0 || px >= nx) continue;
                 const double wI = pweight(w, nzc, nxc, pz, px, Z, X);
                 if (wI == 0.0) continue;
+                const double tp = pdeficit(w, nxc, pz, px);
+                double as = A.S(pz, px) * (1.0 - tp);
 #pragma unroll
                 for (int dz = -1; dz <= 1; dz++) {
                     const int qz = pz + dz;
@@ -123,21 +146,45 @@ k_galerkin(Op A, int nzc, int nxc, Weights w, double *__restrict__ Cc, double *_
                     for (int dx = -1; dx <= 1; dx++) {
                         const int qx = px + dx;
                         if (qx < 0 || qx >= nx) continue;
-                        const double a = (dz == 0 && dx == 0) ? A.diag(pz, px) : -A.g(pz, px, dz, dx);
+                        const bool self = (dz == 0 && dx == 0);
+                        const double gpq = self ? 0.0 : A.g(pz, px, dz, dx);
+                        const double a = self ? A.diag(pz, px) : -gpq;
                         if (a == 0.0) continue;
+                        if (!self) as += gpq * (pdeficit(w, nxc, qz, qx) - tp);
                         const double wa = wI * a;
 #pragma unroll
-                        for (int j = 0; j < 5; j++) acc[j] += wa * pweight(w, nzc, nxc, qz, qx, Jz[j], Jx[j]);
+                        for (int j = 0; j < 4; j++) acc[j] += wa * pweight(w, nzc, nxc, qz, qx, Jz[j], Jx[j]);
                     }
                 }
+                sabs += wI * as;
             }
         }
         const size_t i = (size_t)Z * nxc + X;
-        Cc[i] = acc[0];
-        Ec[i] = (X + 1 < nxc) ? -acc[1] : 0.0;
-        Nc[i] = (Z + 1 < nzc) ? -acc[2] : 0.0;
-        NEc[i] = (Z + 1 < nzc && X + 1 < nxc) ? -acc[3] : 0.0;
-        NWc[i] = (Z + 1 < nzc && X > 0) ? -acc[4] : 0.0;
+        Sc[i] = sabs > 0.0 ? sabs : 0.0;
+        Ec[i] = (X + 1 < nxc) ? -acc[0] : 0.0;
+        Nc[i] = (Z + 1 < nzc) ? -acc[1] : 0.0;
+        NEc[i] = (Z + 1 < nzc && X + 1 < nxc) ? -acc[2] : 0.0;
+        NWc[i] = (Z + 1 < nzc && X > 0) ? -acc[3] : 0.0;
+    }
+}
+
+// C = S + sum of the eight couplings (needs every point's E,N,NE,NW, hence a second pass)
+__global__ void __launch_bounds__(kBlock)
+k_coarse_diag(Coarse9 v, double *__restrict__ C)
+{
+    const C9 A{v};
+    const Tiles tiles(v.nz, v.nx);
+    for (long long t = blockIdx.x; t < tiles.ntiles; t += gridDim.x) {
+        int z, x;
+        tiles.cell(t, z, x);
+        if (z >= v.nz || x >= v.nx) continue;
+        double s = A.S(z, x);
+#pragma unroll
+        for (int dz = -1; dz <= 1; dz++)
+#pragma unroll
+            for (int dx = -1; dx <= 1; dx++)
+                if (dz || dx) s += A.g(z, x, dz, dx);
+        C[(size_t)z * v.nx + x] = s;
     }
 }
 
@@ -203,9 +250,10 @@ void mg_allocate(Solver &s)
         Level &f = s.levels.back();
         Level c;
         c.nz = (f.nz + 1) / 2; c.nx = (f.nx + 1) / 2; c.n = (size_t)c.nz * c.nx;
-        double **wp[8] = {&f.w.hw, &f.w.he, &f.w.vs, &f.w.vn, &f.w.csw, &f.w.cse, &f.w.cnw, &f.w.cne};
+        double **wp[11] = {&f.w.hw, &f.w.he, &f.w.vs, &f.w.vn, &f.w.csw, &f.w.cse, &f.w.cnw, &f.w.cne,
+                           &f.w.th, &f.w.tv, &f.w.tc};
         for (auto p : wp) alloc_d(p, c.n);
-        double **cp[8] = {&c.C, &c.E, &c.N, &c.NE, &c.NW, &c.x, &c.b, &c.r};
+        double **cp[9] = {&c.C, &c.S, &c.E, &c.N, &c.NE, &c.NW, &c.x, &c.b, &c.r};
         for (auto p : cp) alloc_d(p, c.n);
         s.levels.push_back(c);
     }
@@ -214,7 +262,7 @@ void mg_allocate(Solver &s)
         // single-level hierarchy by smoothing + dense solve of a 9-point copy of the fine operator.
         Level c;
         c.nz = s.nz; c.nx = s.nx; c.n = s.n;
-        double **cp[8] = {&c.C, &c.E, &c.N, &c.NE, &c.NW, &c.x, &c.b, &c.r};
+        double **cp[9] = {&c.C, &c.S, &c.E, &c.N, &c.NE, &c.NW, &c.x, &c.b, &c.r};
         for (auto p : cp) alloc_d(p, c.n);
         s.levels.push_back(c);
         s.levels[0].w = Weights{};   // marks "identity transfer"
@@ -227,8 +275,8 @@ void mg_allocate(Solver &s)
 void mg_free(Solver &s)
 {
     for (auto &l : s.levels) {
-        double *ptrs[16] = {l.C, l.E, l.N, l.NE, l.NW, l.x, l.b, l.r, l.w.hw, l.w.he, l.w.vs, l.w.vn,
-                            l.w.csw, l.w.cse, l.w.cnw, l.w.cne};
+        double *ptrs[20] = {l.C, l.S, l.E, l.N, l.NE, l.NW, l.x, l.b, l.r, l.w.hw, l.w.he, l.w.vs, l.w.vn,
+                            l.w.csw, l.w.cse, l.w.cnw, l.w.cne, l.w.th, l.w.tv, l.w.tc};
         for (double *p : ptrs)
             if (p) cudaFree(p);
     }
@@ -239,13 +287,14 @@ void mg_free(Solver &s)
 }
 
 // copy of the fine 5-point operator as a 9-point one (only for maps with <= kCoarsestCells cells)
-__global__ void k_fine_as_coarse(Fine5 v, double *C, double *E, double *N, double *NE, double *NW)
+__global__ void k_fine_as_coarse(Fine5 v, double *C, double *S, double *E, double *N, double *NE, double *NW)
 {
     const F5 A{v};
     const int n = v.nz * v.nx;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const int z = i / v.nx, x = i % v.nx;
         C[i] = A.diag(z, x);
+        S[i] = A.S(z, x);
         E[i] = A.g(z, x, 0, 1);
         N[i] = A.g(z, x, 1, 0);
         NE[i] = 0.0;
@@ -259,14 +308,15 @@ static void build_next(Solver &s, const Op &A, Level &f, Level &c)
     const int grid = grid_for(s, c.nz, c.nx, 8);
     LAUNCH((k_weights_edges<Op>), grid, kBlock, 0, s.stream, A, c.nz, c.nx, f.w);
     LAUNCH((k_weights_centres<Op>), grid, kBlock, 0, s.stream, A, c.nz, c.nx, f.w);
-    LAUNCH((k_galerkin<Op>), grid, kBlock, 0, s.stream, A, c.nz, c.nx, f.w, c.C, c.E, c.N, c.NE, c.NW);
+    LAUNCH((k_galerkin<Op>), grid, kBlock, 0, s.stream, A, c.nz, c.nx, f.w, c.S, c.E, c.N, c.NE, c.NW);
+    LAUNCH(k_coarse_diag, grid, kBlock, 0, s.stream, c.view9(), c.C);
 }
 
 void mg_setup(Solver &s)
 {
     if (s.levels[0].w.hw == nullptr) {
         Level &c = s.levels[1];
-        LAUNCH(k_fine_as_coarse, 1, 64, 0, s.stream, s.view5(), c.C, c.E, c.N, c.NE, c.NW);
+        LAUNCH(k_fine_as_coarse, 1, 64, 0, s.stream, s.view5(), c.C, c.S, c.E, c.N, c.NE, c.NW);
     } else {
         build_next(s, F5{s.view5()}, s.levels[0], s.levels[1]);
         for (size_t l = 1; l + 1 < s.levels.size(); l++)

@@ -53,11 +53,11 @@ k_spmv5(Fine5 v, const double *__restrict__ d, double *__restrict__ q, PcgState 
         const size_t i = (size_t)z * nx + xx;
         const double tl = A.left(z, xx), tr = A.right(z, xx), td = A.down(z, xx), tu = A.up(z, xx);
         const double di = d[i];
-        double s = ((tl + tr) + (td + tu)) * di;
-        if (xx > 0) s -= tl * d[i - 1];
-        if (xx + 1 < nx) s -= tr * d[i + 1];
-        if (z > 0) s -= td * d[i - nx];
-        if (z + 1 < nz) s -= tu * d[i + nx];
+        // difference form (boundary faces: homogeneous Dirichlet value 0)
+        double s = tl * (di - (xx > 0 ? d[i - 1] : 0.0));
+        s += tr * (di - (xx + 1 < nx ? d[i + 1] : 0.0));
+        s += td * (di - (z > 0 ? d[i - nx] : 0.0));
+        s += tu * (di - (z + 1 < nz ? d[i + nx] : 0.0));
         q[i] = s;
         acc[0] += di * s;
     }
@@ -122,11 +122,11 @@ k_true_residual(Fine5 v, BoundaryValues bv, const double *__restrict__ x, double
         const size_t i = (size_t)z * nx + xx;
         const double tl = A.left(z, xx), tr = A.right(z, xx), td = A.down(z, xx), tu = A.up(z, xx);
         const double dg = (tl + tr) + (td + tu);
-        double s = -dg * x[i];
-        s += tl * (xx > 0 ? x[i - 1] : bv.left);
-        s += tr * (xx + 1 < nx ? x[i + 1] : bv.right);
-        s += td * (z > 0 ? x[i - nx] : bv.bottom);
-        s += tu * (z + 1 < nz ? x[i + nx] : bv.top);
+        const double xi = x[i];
+        double s = tl * ((xx > 0 ? x[i - 1] : bv.left) - xi);
+        s += tr * ((xx + 1 < nx ? x[i + 1] : bv.right) - xi);
+        s += td * ((z > 0 ? x[i - nx] : bv.bottom) - xi);
+        s += tu * ((z + 1 < nz ? x[i + nx] : bv.top) - xi);
         r[i] = s;
         acc[0] += s * s;
         acc[1] += s * s / dg;

@@ -117,6 +117,14 @@ APM_LCL_API int apm_lcl_solver_solve(apm_lcl_solver *s, const apm_lcl_params *p,
 APM_LCL_API int apm_lcl_solve(const apm_lcl_params *p, const double *aperture, int nx, int nz, int device,
                   apm_lcl_fields *out, apm_lcl_scalars *sc);
 
+/* File-level entry point: what `apm-lcl-model.exe file.inp` does (APERTURE_MAP_FLOW.F:1-51).  Reads the
+ * initialization file (OPEN_IO IO_MODULE.F:51, READ_MASTER APERTURE_MAP_FLOW.F:191), the aperture map
+ * (READ_DATA_MAP MAP_MODULE.F:18), runs the hot path on `device` and writes the log, stat (csv+yaml),
+ * aperture, flow-x/z/m, pressure and VTK files in the reference's formats.  The transcript the
+ * reference prints to stdout is returned in `log` (NUL terminated, truncated at the front if longer
+ * than log_cap).  Returns 0, or 1 with the reference's error messages in the transcript. */
+APM_LCL_API int apm_lcl_run_file(const char *inp_path, int device, char *log, size_t log_cap);
+
 /* Kernel-level entry points used by the parity tests -------------------------------------- */
 
 /* COEF + FLOW_BOUNDARY: writes WIDTH[nz*nx], TRX[nz][nx+1] (faces 0..NX of each row) and

@@ -75,8 +75,7 @@ EXPORTS = (
     "apm_lcl_version", "apm_lcl_last_error", "apm_lcl_last_launch_count", "apm_lcl_default_params",
     "apm_lcl_solver_create", "apm_lcl_solver_destroy", "apm_lcl_solver_solve", "apm_lcl_solve",
     "apm_lcl_conductance", "apm_lcl_solver_device_field", "apm_lcl_solver_time_kernel",
-    "apm_lcl_run_file", "apm_lcl_bulk_solve",
-    "apm_lcl_dist_unique_id", "apm_lcl_dist_create", "apm_lcl_dist_solve", "apm_lcl_dist_destroy",
+    "apm_lcl_run_file",
 )
 
 _lib = None
@@ -115,6 +114,8 @@ def bind(lib):
                                                 C.POINTER(C.c_size_t)]
     lib.apm_lcl_solver_time_kernel.argtypes = [C.c_void_p, C.c_char_p, C.c_int,
                                                C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    lib.apm_lcl_run_file.argtypes = [C.c_char_p, C.c_int, C.c_char_p, C.c_size_t]
+    lib.apm_lcl_run_file.restype = C.c_int
     return lib
 
 

@@ -14,9 +14,10 @@ OBJ = os.path.join(HERE, "build")
 
 def build(force=False):
     os.makedirs(OBJ, exist_ok=True)
-    srcs = sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cu"))
+    srcs = sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC)
+                  if f.endswith(".cu") or (f.endswith(".cpp") and f != "main.cpp"))
     srcs.append(os.path.join(HERE, "sim_globals.cpp"))
-    deps = srcs + [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cuh")] + \
+    deps = srcs + [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".hpp"))] + \
         [os.path.join(HERE, "cuda_sim.h"), os.path.join(ROOT, "include", "apm_lcl.h")]
     if not force and os.path.exists(LIB) and all(os.path.getmtime(d) <= os.path.getmtime(LIB) for d in deps):
         return LIB

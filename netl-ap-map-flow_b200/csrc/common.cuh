@@ -159,7 +159,8 @@ void mg_setup(Solver &s);   // weights + Galerkin operators + coarsest inverse, 
 // z = M^-1 r on the fine level.  The first kernel also accumulates ||r||^2 and r^T D^-1 r into st
 // (convergence test; with init they become the norms of the right-hand side) and the last one r.z
 // (-> st->rz, st->beta).  Every kernel is a no-op once st->converged or st->failed is set.
-void mg_vcycle(Solver &s, const double *r, double *z, PcgState *st, bool init);
+// ztmp is scratch (the pre-smoothed iterate), the result lands in zout.
+void mg_vcycle(Solver &s, const double *r, double *ztmp, double *zout, PcgState *st, bool init);
 
 // pcg.cu ---------------------------------------------------------------------------------------
 struct BoundaryValues {

@@ -170,6 +170,236 @@ k_residual9(Coarse9 v, const double *__restrict__ b, const double *__restrict__ 
     }
 }
 
+// ------------------------------------------------------------------- fused tile smoothers
+// value the interpolation P e gives at fine point (z,x)
+__device__ __forceinline__ double prolong_value(const Weights &w, const double *__restrict__ e, int nzc, int nxc,
+                                                int z, int x)
+{
+    const int bz = z >> 1, bx = x >> 1;
+    const size_t b = (size_t)bz * nxc + bx;
+    const bool Xp = bx + 1 < nxc, Zp = bz + 1 < nzc;
+    const double e00 = e[b];
+    if (!(z & 1)) {
+        if (!(x & 1)) return e00;
+        return w.hw[b] * e00 + (Xp ? w.he[b] * e[b + 1] : 0.0);
+    }
+    if (!(x & 1)) return w.vs[b] * e00 + (Zp ? w.vn[b] * e[b + nxc] : 0.0);
+    return (w.csw[b] * e00 + (Xp ? w.cse[b] * e[b + 1] : 0.0)) +
+           ((Zp ? w.cnw[b] * e[b + nxc] : 0.0) + ((Zp && Xp) ? w.cne[b] * e[b + nxc + 1] : 0.0));
+}
+
+constexpr int kSmTZ = 16, kSmTX = 64;   // smoother tile: 1024 points, 256 threads
+
+// All four colours and all `nu` sweeps of one 9-point level in ONE launch.  Each block owns a
+// 16x64 tile, keeps x (+1 halo) in shared memory and runs four-colour Gauss-Seidel on it; halo
+// values stay frozen during the launch (hybrid GS: Jacobi between tiles, GS inside -- a regular
+// splitting, and the backward variant is its transpose, so the cycle stays symmetric).
+// ZERO_INIT: x starts from 0 (down leg; nothing is read).  PROLONG: x starts from x + P e (up leg).
+template <bool ZERO_INIT, bool PROLONG>
+__global__ void __launch_bounds__(256)
+k_smooth9(Coarse9 v, const double *__restrict__ b, const double *__restrict__ xin, double *__restrict__ xout, int nu,
+          int forward, Weights w, const double *__restrict__ e, int nzc, int nxc, const PcgState *st)
+{
+    if (stopped(st)) return;
+    const C9 A{v};
+    const int nz = v.nz, nx = v.nx;
+    constexpr int W = kSmTX + 2, H = kSmTZ + 2;
+    __shared__ double sx[H * W];
+    const int tiles_x = (nx + kSmTX - 1) / kSmTX, tiles_z = (nz + kSmTZ - 1) / kSmTZ;
+    const int tid = threadIdx.x;
+    for (long long t = blockIdx.x; t < (long long)tiles_x * tiles_z; t += gridDim.x) {
+        const int z0 = (int)(t / tiles_x) * kSmTZ, x0 = (int)(t % tiles_x) * kSmTX;
+        for (int k = tid; k < H * W; k += blockDim.x) {
+            const int z = z0 + k / W - 1, xx = x0 + k % W - 1;
+            double val = 0.0;
+            if (!ZERO_INIT && z >= 0 && z < nz && xx >= 0 && xx < nx) {
+                val = xin[(size_t)z * nx + xx];     // never the array this launch writes: other tiles read it
+                if (PROLONG) val += prolong_value(w, e, nzc, nxc, z, xx);
+            }
+            sx[k] = val;
+        }
+        __syncthreads();
+        const int a = tid >> 5, c = tid & 31;
+        for (int sweep = 0; sweep < nu; sweep++)
+            for (int step = 0; step < 4; step++) {
+                const int col = forward ? step : 3 - step;
+                const int lz = 2 * a + (col >> 1), lx = 2 * c + (col & 1);
+                const int z = z0 + lz, xx = x0 + lx;
+                if (z < nz && xx < nx) {
+                    const size_t i = (size_t)z * nx + xx;
+                    const double *p = &sx[(lz + 1) * W + lx + 1];
+                    double s = b[i];
+                    s += A.g(z, xx, 0, -1) * p[-1] + A.g(z, xx, 0, 1) * p[1];
+                    s += A.g(z, xx, -1, 0) * p[-W] + A.g(z, xx, 1, 0) * p[W];
+                    s += A.g(z, xx, -1, -1) * p[-W - 1] + A.g(z, xx, -1, 1) * p[-W + 1];
+                    s += A.g(z, xx, 1, -1) * p[W - 1] + A.g(z, xx, 1, 1) * p[W + 1];
+                    sx[(lz + 1) * W + lx + 1] = s / A.diag(z, xx);
+                }
+                __syncthreads();
+            }
+        for (int k = tid; k < kSmTZ * kSmTX; k += blockDim.x) {
+            const int lz = k / kSmTX, lx = k % kSmTX;
+            const int z = z0 + lz, xx = x0 + lx;
+            if (z < nz && xx < nx) xout[(size_t)z * nx + xx] = sx[(lz + 1) * W + lx + 1];
+        }
+        __syncthreads();
+    }
+}
+
+// Fine level, down leg: one EXACT red/black sweep from a zero guess in one launch.
+// red = b/diag needs no neighbour, so the red values of the halo ring are recomputed from b and the
+// faces instead of being exchanged; black then sees exactly what the two-pass version saw.
+// ||b||^2 and b^T D^-1 b (= the PCG residual norms) ride along.
+__global__ void __launch_bounds__(256)
+k_smooth5_down(Fine5 v, const double *__restrict__ b, double *__restrict__ x, PcgState *st, int init,
+               double *partials, unsigned int *counter)
+{
+    if (stopped(st)) return;
+    const F5 A{v};
+    const int nz = v.nz, nx = v.nx;
+    constexpr int W = kSmTX + 2, H = kSmTZ + 2;
+    __shared__ double sx[H * W];
+    const int tiles_x = (nx + kSmTX - 1) / kSmTX, tiles_z = (nz + kSmTZ - 1) / kSmTZ;
+    const int tid = threadIdx.x;
+    double acc[2] = {0.0, 0.0};
+    for (long long t = blockIdx.x; t < (long long)tiles_x * tiles_z; t += gridDim.x) {
+        const int z0 = (int)(t / tiles_x) * kSmTZ, x0 = (int)(t % tiles_x) * kSmTX;
+        // red pass over tile + halo (colour 0 = (z+x) even); black cells start at 0
+        for (int k = tid; k < H * W; k += blockDim.x) {
+            const int lz = k / W - 1, lx = k % W - 1;
+            const int z = z0 + lz, xx = x0 + lx;
+            double val = 0.0;
+            if (z >= 0 && z < nz && xx >= 0 && xx < nx) {
+                const bool interior = lz >= 0 && lz < kSmTZ && lx >= 0 && lx < kSmTX;
+                const bool red = ((z + xx) & 1) == 0;
+                if (red || interior) {
+                    const double bi = b[(size_t)z * nx + xx];
+                    const double inv = 1.0 / A.diag(z, xx);
+                    if (red) val = bi * inv;
+                    if (interior) { acc[0] += bi * bi; acc[1] += bi * bi * inv; }
+                }
+            }
+            sx[k] = val;
+        }
+        __syncthreads();
+        // black pass, tile interior only
+        for (int k = tid; k < kSmTZ * kSmTX / 2; k += blockDim.x) {
+            const int lz = k / (kSmTX / 2);
+            const int z = z0 + lz;
+            const int lx = 2 * (k % (kSmTX / 2)) + ((z + 1) & 1);   // (z + x) odd, x0 is even
+            const int xx = x0 + lx;
+            if (z < nz && xx < nx) {
+                const size_t i = (size_t)z * nx + xx;
+                const double *p = &sx[(lz + 1) * W + lx + 1];
+                const double tl = A.left(z, xx), tr = A.right(z, xx), td = A.down(z, xx), tu = A.up(z, xx);
+                double s = b[i];
+                if (xx > 0) s += tl * p[-1];
+                if (xx + 1 < nx) s += tr * p[1];
+                if (z > 0) s += td * p[-W];
+                if (z + 1 < nz) s += tu * p[W];
+                sx[(lz + 1) * W + lx + 1] = s / ((tl + tr) + (td + tu));
+            }
+        }
+        __syncthreads();
+        for (int k = tid; k < kSmTZ * kSmTX; k += blockDim.x) {
+            const int lz = k / kSmTX, lx = k % kSmTX;
+            const int z = z0 + lz, xx = x0 + lx;
+            if (z < nz && xx < nx) x[(size_t)z * nx + xx] = sx[(lz + 1) * W + lx + 1];
+        }
+        __syncthreads();
+    }
+    grid_sum_finalize<2>(acc, partials, counter, [=](const double(&tot)[2]) {
+        st->rr = tot[0];
+        st->rs = tot[1];
+        if (init) {
+            st->bb = tot[0];
+            st->bs = tot[1];
+        } else if (tot[0] <= st->tol2 * st->bb && tot[1] <= st->tol2 * st->bs) {
+            // Residual norms are met.  Keep iterating only while every update still shrinks the
+            // largest pointwise pressure change: that is how weakly connected cells (which global
+            // norms do not see) reach 1e-6.  If the change grows twice in a row (or after 12 such
+            // extra iterations) what is left are floating pockets, so stop.
+            st->res_ok += 1;
+            if ((st->dx <= st->dx_tol && st->dx_prev <= st->dx_tol) || (st->dx > st->dx_prev && st->dx_prev > st->dx_prev2) || st->res_ok > 12)
+                st->converged = 1;
+        }
+        if (!(tot[0] == tot[0]) || !(tot[1] == tot[1])) st->failed = 1;
+    });
+}
+
+// Fine level, up leg: x += P e, then one EXACT black/red sweep, and b.x (= r.z of PCG) in one launch.
+// The tile carries a 2-cell halo of x + P e so the black cells of the first halo ring can be updated
+// redundantly and the red cells of the tile see exactly what the two-pass version saw.
+__global__ void __launch_bounds__(256)
+k_smooth5_up(Fine5 v, const double *__restrict__ b, const double *__restrict__ xin, double *__restrict__ xout, Weights w,
+             const double *__restrict__ e, int nzc, int nxc, PcgState *st, int init, double *partials, unsigned int *counter)
+{
+    if (stopped(st)) return;
+    const F5 A{v};
+    const int nz = v.nz, nx = v.nx;
+    constexpr int W = kSmTX + 4, H = kSmTZ + 4;
+    __shared__ double sx[H * W];
+    const int tiles_x = (nx + kSmTX - 1) / kSmTX, tiles_z = (nz + kSmTZ - 1) / kSmTZ;
+    const int tid = threadIdx.x;
+    double acc[2] = {0.0, 0.0};
+    for (long long t = blockIdx.x; t < (long long)tiles_x * tiles_z; t += gridDim.x) {
+        const int z0 = (int)(t / tiles_x) * kSmTZ, x0 = (int)(t % tiles_x) * kSmTX;
+        for (int k = tid; k < H * W; k += blockDim.x) {
+            const int z = z0 + k / W - 2, xx = x0 + k % W - 2;
+            double val = 0.0;
+            if (z >= 0 && z < nz && xx >= 0 && xx < nx) val = xin[(size_t)z * nx + xx] + prolong_value(w, e, nzc, nxc, z, xx);
+            sx[k] = val;
+        }
+        __syncthreads();
+        // black pass over tile + first halo ring
+        constexpr int W1 = kSmTX + 2, H1 = kSmTZ + 2;
+        for (int k = tid; k < H1 * W1; k += blockDim.x) {
+            const int lz = k / W1 - 1, lx = k % W1 - 1;
+            const int z = z0 + lz, xx = x0 + lx;
+            if (z >= 0 && z < nz && xx >= 0 && xx < nx && ((z + xx) & 1) == 1) {
+                const size_t i = (size_t)z * nx + xx;
+                const double *p = &sx[(lz + 2) * W + lx + 2];
+                const double tl = A.left(z, xx), tr = A.right(z, xx), td = A.down(z, xx), tu = A.up(z, xx);
+                double s = b[i];
+                if (xx > 0) s += tl * p[-1];
+                if (xx + 1 < nx) s += tr * p[1];
+                if (z > 0) s += td * p[-W];
+                if (z + 1 < nz) s += tu * p[W];
+                sx[(lz + 2) * W + lx + 2] = s / ((tl + tr) + (td + tu));
+            }
+        }
+        __syncthreads();
+        // red pass, tile interior, and the dot product over every interior cell
+        for (int k = tid; k < kSmTZ * kSmTX; k += blockDim.x) {
+            const int lz = k / kSmTX, lx = k % kSmTX;
+            const int z = z0 + lz, xx = x0 + lx;
+            if (z < nz && xx < nx) {
+                const size_t i = (size_t)z * nx + xx;
+                const double *p = &sx[(lz + 2) * W + lx + 2];
+                const double bi = b[i];
+                double xi = p[0];
+                if (((z + xx) & 1) == 0) {
+                    const double tl = A.left(z, xx), tr = A.right(z, xx), td = A.down(z, xx), tu = A.up(z, xx);
+                    double s = bi;
+                    if (xx > 0) s += tl * p[-1];
+                    if (xx + 1 < nx) s += tr * p[1];
+                    if (z > 0) s += td * p[-W];
+                    if (z + 1 < nz) s += tu * p[W];
+                    xi = s / ((tl + tr) + (td + tu));
+                }
+                xout[i] = xi;       // out of place: neighbouring tiles still read xin for their halos
+                acc[0] += bi * xi;
+            }
+        }
+        __syncthreads();
+    }
+    grid_sum_finalize<2>(acc, partials, counter, [=](const double(&tot)[2]) {
+        st->rz_new = tot[0];
+        st->beta = init ? 0.0 : tot[0] / st->rz;
+        st->rz = tot[0];
+    });
+}
+
 // ------------------------------------------------------------------------------------ transfers
 // bc = P^T r : thread per coarse point gathers its 3x3 fine neighbourhood
 __global__ void __launch_bounds__(kBlock)
@@ -287,6 +517,29 @@ double bench_launch_cycle(Solver &s, const std::string &name)
     double *part = s.red + 16 * kMaxPartials;
     unsigned int *cnt = s.red_counters + 4;
     const double n = (double)s.n;
+    auto tile_grid = [&](int nz, int nx) {
+        long long tiles = (long long)div_up(nx, kSmTX) * div_up(nz, kSmTZ);
+        long long cap = (long long)s.num_sms * 6;
+        if (cap > kMaxPartials) cap = kMaxPartials;
+        return (int)(tiles < cap ? tiles : cap);
+    };
+    if (name == "smooth_down") {
+        LAUNCH(k_smooth5_down, tile_grid(s.nz, s.nx), 256, 0, s.stream, v5, (const double *)s.r, s.z, s.state, 0, part, cnt);
+        return 32.0 * n;   // b, tx, tz in; x out
+    }
+    if (name == "smooth_up" && s.levels.size() > 1 && s.levels[0].w.hw) {
+        Level &c = s.levels[1];
+        LAUNCH(k_smooth5_up, tile_grid(s.nz, s.nx), 256, 0, s.stream, v5, (const double *)s.r, (const double *)s.z, s.q,
+               s.levels[0].w, (const double *)c.r, c.nz, c.nx, s.state, 0, part + 4 * kMaxPartials, cnt + 1);
+        return 40.0 * n + (8.0 + 64.0) * (double)c.n;   // x, b, tx, tz in; x out; coarse e + 8 weights
+    }
+    if (name == "smooth9_l1" && s.levels.size() > 2) {
+        Level &f = s.levels[1];
+        LAUNCH((k_smooth9<true, false>), tile_grid(f.nz, f.nx), 256, 0, s.stream, f.view9(), (const double *)f.b,
+               (const double *)nullptr, f.x, s.nu_coarse, 1, Weights{}, (const double *)nullptr, 0, 0,
+               (const PcgState *)s.state);
+        return 56.0 * (double)f.n;   // b, C, E, N, NE, NW in; x out (couplings re-read from L1/L2 per sweep)
+    }
     if (name == "gs5_first") {
         LAUNCH((k_gs5<GS_FIRST>), g0, kBlock, 0, s.stream, v5, (const double *)s.r, s.z, 0, s.state, 0, part, cnt);
         return 32.0 * n;   // b, tx, tz in; x out
@@ -318,7 +571,7 @@ double bench_launch_cycle(Solver &s, const std::string &name)
         }
     }
     if (name == "vcycle") {
-        mg_vcycle(s, s.r, s.z, s.state, false);
+        mg_vcycle(s, s.r, s.z, s.q, s.state, false);
         return 0.0;
     }
     return -1.0;
@@ -339,7 +592,7 @@ static void smooth9(Solver &s, Level &l, bool forward, int sweeps, PcgState *st)
         }
 }
 
-void mg_vcycle(Solver &s, const double *r, double *z, PcgState *st, bool init_flag)
+void mg_vcycle(Solver &s, const double *r, double *ztmp, double *zout, PcgState *st, bool init_flag)
 {
     const int init = init_flag ? 1 : 0;
     const Fine5 v5 = s.view5();
@@ -347,62 +600,56 @@ void mg_vcycle(Solver &s, const double *r, double *z, PcgState *st, bool init_fl
     double *part = s.red + 16 * kMaxPartials;   // slots 16.. belong to the cycle
     unsigned int *cnt = s.red_counters + 4;
     const size_t nlev = s.levels.size();
+    auto tile_grid = [&](int nz, int nx) {
+        long long tiles = (long long)div_up(nx, kSmTX) * div_up(nz, kSmTZ);
+        long long cap = (long long)s.num_sms * 6;
+        if (cap > kMaxPartials) cap = kMaxPartials;
+        return (int)(tiles < cap ? tiles : cap);
+    };
 
     if (s.levels[0].w.hw == nullptr) {   // map small enough for the dense solve alone
         Level &c = s.levels[1];
-        LAUNCH(k_coarse_solve, 1, 64, c.n * sizeof(double), s.stream, s.coarse_inv, s.coarse_scale, r, z, (int)c.n, st);
-        LAUNCH(k_dot_norms, 1, kBlock, 0, s.stream, r, z, v5, st, init, part, cnt);
+        LAUNCH(k_coarse_solve, 1, 64, c.n * sizeof(double), s.stream, s.coarse_inv, s.coarse_scale, r, zout, (int)c.n, st);
+        LAUNCH(k_dot_norms, 1, kBlock, 0, s.stream, r, (const double *)zout, v5, st, init, part, cnt);
         return;
     }
 
-    // ---- down leg, fine level
-    LAUNCH((k_gs5<GS_FIRST>), g0, kBlock, 0, s.stream, v5, r, z, 0, st, init, part, cnt);
-    LAUNCH((k_gs5<GS_PLAIN>), g0, kBlock, 0, s.stream, v5, r, z, 1, st, init, part, cnt);
-    for (int k = 1; k < s.nu_fine; k++) {
-        LAUNCH((k_gs5<GS_PLAIN>), g0, kBlock, 0, s.stream, v5, r, z, 0, st, init, part, cnt);
-        LAUNCH((k_gs5<GS_PLAIN>), g0, kBlock, 0, s.stream, v5, r, z, 1, st, init, part, cnt);
-    }
-    LAUNCH(k_residual5, g0, kBlock, 0, s.stream, v5, r, (const double *)z, s.q, st);
+    // The fused smoothers are out of place (a tile must not see its neighbours' new values through
+    // the halo), so each level ping-pongs: down leg x -> level.x, up leg result -> level.r (the
+    // residual it held has been restricted by then).  Fine level: ztmp after the down leg, zout final;
+    // zout doubles as the fine residual buffer in between.
+    LAUNCH(k_smooth5_down, tile_grid(s.nz, s.nx), 256, 0, s.stream, v5, r, ztmp, st, init, part, cnt);
+    LAUNCH(k_residual5, g0, kBlock, 0, s.stream, v5, r, (const double *)ztmp, zout, st);
     {
         Level &c = s.levels[1];
-        LAUNCH(k_restrict, grid_for(s, c.nz, c.nx, 8), kBlock, 0, s.stream, s.levels[0].w, (const double *)s.q,
+        LAUNCH(k_restrict, grid_for(s, c.nz, c.nx, 8), kBlock, 0, s.stream, s.levels[0].w, (const double *)zout,
                s.nz, s.nx, c.b, c.nz, c.nx, st);
     }
-    // ---- down leg, coarse levels
+    const Weights now{};
     for (size_t l = 1; l + 1 < nlev; l++) {
         Level &f = s.levels[l], &c = s.levels[l + 1];
-        CUDA_CHECK(cudaMemsetAsync(f.x, 0, f.n * sizeof(double), s.stream));
-        smooth9(s, f, true, s.nu_coarse, st);
+        LAUNCH((k_smooth9<true, false>), tile_grid(f.nz, f.nx), 256, 0, s.stream, f.view9(), (const double *)f.b,
+               (const double *)nullptr, f.x, s.nu_coarse, 1, now, (const double *)nullptr, 0, 0, (const PcgState *)st);
         LAUNCH(k_residual9, grid_for(s, f.nz, f.nx, 8), kBlock, 0, s.stream, f.view9(), (const double *)f.b,
                (const double *)f.x, f.r, st);
         LAUNCH(k_restrict, grid_for(s, c.nz, c.nx, 8), kBlock, 0, s.stream, f.w, (const double *)f.r, f.nz, f.nx,
                c.b, c.nz, c.nx, st);
     }
-    // ---- coarsest: dense solve
-    {
+    {   // coarsest: dense solve, result in .r like every other level's up-leg result
         Level &c = s.levels[nlev - 1];
         LAUNCH(k_coarse_solve, 1, 64, c.n * sizeof(double), s.stream, s.coarse_inv, s.coarse_scale,
-               (const double *)c.b, c.x, (int)c.n, st);
+               (const double *)c.b, c.r, (int)c.n, st);
     }
-    // ---- up leg, coarse levels
     for (size_t l = nlev - 2; l >= 1; l--) {
         Level &f = s.levels[l], &c = s.levels[l + 1];
-        LAUNCH(k_prolong_add, grid_for(s, c.nz, c.nx, 8), kBlock, 0, s.stream, f.w, (const double *)c.x, c.nz, c.nx,
-               f.x, f.nz, f.nx, st);
-        smooth9(s, f, false, s.nu_coarse, st);
+        LAUNCH((k_smooth9<false, true>), tile_grid(f.nz, f.nx), 256, 0, s.stream, f.view9(), (const double *)f.b,
+               (const double *)f.x, f.r, s.nu_coarse, 0, f.w, (const double *)c.r, c.nz, c.nx, (const PcgState *)st);
     }
-    // ---- up leg, fine level
     {
         Level &c = s.levels[1];
-        LAUNCH(k_prolong_add, grid_for(s, c.nz, c.nx, 8), kBlock, 0, s.stream, s.levels[0].w, (const double *)c.x,
-               c.nz, c.nx, z, s.nz, s.nx, st);
+        LAUNCH(k_smooth5_up, tile_grid(s.nz, s.nx), 256, 0, s.stream, v5, r, (const double *)ztmp, zout, s.levels[0].w,
+               (const double *)c.r, c.nz, c.nx, st, init, part + 4 * kMaxPartials, cnt + 1);
     }
-    for (int k = 1; k < s.nu_fine; k++) {
-        LAUNCH((k_gs5<GS_PLAIN>), g0, kBlock, 0, s.stream, v5, r, z, 1, st, init, part, cnt);
-        LAUNCH((k_gs5<GS_PLAIN>), g0, kBlock, 0, s.stream, v5, r, z, 0, st, init, part, cnt);
-    }
-    LAUNCH((k_gs5<GS_PLAIN>), g0, kBlock, 0, s.stream, v5, r, z, 1, st, init, part, cnt);
-    LAUNCH((k_gs5<GS_LAST>), g0, kBlock, 0, s.stream, v5, r, z, 0, st, init, part + 4 * kMaxPartials, cnt + 1);
 }
 
 }   // namespace lcl

@@ -152,7 +152,7 @@ double bench_launch_pcg(Solver &s, const std::string &name)
         return 48.0 * n;
     }
     if (name == "direction") {
-        LAUNCH(k_direction, g1, 256, 0, s.stream, s.d, (const double *)s.z, s.n, (const PcgState *)s.state, 0);
+        LAUNCH(k_direction, g1, 256, 0, s.stream, s.d, (const double *)s.q, s.n, (const PcgState *)s.state, 0);
         return 24.0 * n;
     }
     return -1.0;
@@ -186,8 +186,10 @@ int pcg_solve(Solver &s, const BoundaryValues &bv, double rel_tol, int max_iter,
     const bool debug = getenv("APM_LCL_DEBUG") != nullptr;
     CUDA_CHECK(cudaMemcpyAsync(s.state, &h, sizeof h, cudaMemcpyHostToDevice, s.stream));
     LAUNCH(k_init_rhs, g0, kBlock, 0, s.stream, v5, bv, s.r, s.x);
-    mg_vcycle(s, s.r, s.z, s.state, true);
-    LAUNCH(k_direction, g1, 256, 0, s.stream, s.d, (const double *)s.z, n, (const PcgState *)s.state, 1);
+    // z = M^-1 r lands in s.q: the cycle is out of place and q (= A d) is dead by then; the next
+    // spmv overwrites it after the direction update has consumed it
+    mg_vcycle(s, s.r, s.z, s.q, s.state, true);
+    LAUNCH(k_direction, g1, 256, 0, s.stream, s.d, (const double *)s.q, n, (const PcgState *)s.state, 1);
 
     int iters = 0, restarts = 0;
     bool done = false;
@@ -204,8 +206,8 @@ int pcg_solve(Solver &s, const BoundaryValues &bv, double rel_tol, int max_iter,
                 LAUNCH(k_spmv5, g0, kBlock, 0, s.stream, v5, (const double *)s.d, s.q, s.state, part, cnt);
                 LAUNCH(k_update, g1, 256, 0, s.stream, s.x, s.r, (const double *)s.d, (const double *)s.q, n,
                        s.state, part + 4 * kMaxPartials, cnt + 5);
-                mg_vcycle(s, s.r, s.z, s.state, false);
-                LAUNCH(k_direction, g1, 256, 0, s.stream, s.d, (const double *)s.z, n, (const PcgState *)s.state, 0);
+                mg_vcycle(s, s.r, s.z, s.q, s.state, false);
+                LAUNCH(k_direction, g1, 256, 0, s.stream, s.d, (const double *)s.q, n, (const PcgState *)s.state, 0);
             }
             poll_state(s);
             if (debug)
@@ -244,9 +246,9 @@ int pcg_solve(Solver &s, const BoundaryValues &bv, double rel_tol, int max_iter,
             h2.converged = 0; h2.failed = 0;
             CUDA_CHECK(cudaMemcpyAsync(s.state, &h2, sizeof h2, cudaMemcpyHostToDevice, s.stream));
             CUDA_CHECK(cudaStreamSynchronize(s.stream));
-            mg_vcycle(s, s.r, s.z, s.state, false);
+            mg_vcycle(s, s.r, s.z, s.q, s.state, false);
             // after this cycle beta = rz_new/rz_old is meaningless: force a steepest-descent restart
-            LAUNCH(k_direction, g1, 256, 0, s.stream, s.d, (const double *)s.z, n, (const PcgState *)s.state, 1);
+            LAUNCH(k_direction, g1, 256, 0, s.stream, s.d, (const double *)s.q, n, (const PcgState *)s.state, 1);
             poll_state(s);
             if (s.state_host->converged) {
                 // the cycle's own test passed on the true residual it was given

@@ -40,6 +40,9 @@ static void solver_free(Solver *s)
     if (s->scal_host) cudaFreeHost(s->scal_host);
     for (auto &e : s->ev)
         if (e) cudaEventDestroy(e);
+#ifndef LCL_CPU_SIM
+    if (s->iter_graph) cudaGraphExecDestroy(s->iter_graph);
+#endif
     if (s->stream) cudaStreamDestroy(s->stream);
     delete s;
 }

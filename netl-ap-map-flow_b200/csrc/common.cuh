@@ -137,6 +137,10 @@ struct Solver {
     double *scal = nullptr;         // misc device scalars (conductance sums, flux reductions)
     double *scal_host = nullptr;    // pinned mirror
     cudaEvent_t ev[6]{};
+#ifndef LCL_CPU_SIM
+    cudaGraphExec_t iter_graph = nullptr;   // one steady-state PCG iteration (spmv, update, V-cycle, direction)
+#endif
+    long long iter_graph_launches = 0;
     int nu_fine = 1, nu_coarse = 2;
     bool have_solution = false;
     apm_lcl_params last_params{};

@@ -190,6 +190,33 @@ __device__ __forceinline__ double prolong_value(const Weights &w, const double *
 
 constexpr int kSmTZ = 16, kSmTX = 64;   // smoother tile: 1024 points, 256 threads
 
+// sx (H x W doubles, H and W even) covers the fine cells from (zr, xr), both even (possibly -2):
+// add P e to it, one thread per coarse 2x2 block so the 8 weights and 4 coarse values are loaded once
+template <int H, int W>
+__device__ __forceinline__ void add_prolongation(double *sx, const Weights &w, const double *__restrict__ e, int nzc,
+                                                 int nxc, int zr, int xr, int nz, int nx)
+{
+    constexpr int BH = H / 2, BW = W / 2;
+    const int bz0 = zr >> 1, bx0 = xr >> 1;   // arithmetic shift: -2 >> 1 == -1
+    for (int k = threadIdx.x; k < BH * BW; k += blockDim.x) {
+        const int bzl = k / BW, bxl = k % BW;
+        const int bz = bz0 + bzl, bx = bx0 + bxl;
+        if (bz < 0 || bx < 0 || bz >= nzc || bx >= nxc) continue;
+        const size_t b = (size_t)bz * nxc + bx;
+        const bool Xp = bx + 1 < nxc, Zp = bz + 1 < nzc;
+        const bool xp = 2 * bx + 1 < nx, zp = 2 * bz + 1 < nz;
+        const double e00 = e[b];
+        const double e01 = Xp ? e[b + 1] : 0.0;
+        const double e10 = Zp ? e[b + nxc] : 0.0;
+        const double e11 = (Zp && Xp) ? e[b + nxc + 1] : 0.0;
+        double *p = &sx[(2 * bzl) * W + 2 * bxl];
+        p[0] += e00;
+        if (xp) p[1] += w.hw[b] * e00 + w.he[b] * e01;
+        if (zp) p[W] += w.vs[b] * e00 + w.vn[b] * e10;
+        if (zp && xp) p[W + 1] += (w.csw[b] * e00 + w.cse[b] * e01) + (w.cnw[b] * e10 + w.cne[b] * e11);
+    }
+}
+
 // All four colours and all `nu` sweeps of one 9-point level in ONE launch.  Each block owns a
 // 16x64 tile, keeps x (+1 halo) in shared memory and runs four-colour Gauss-Seidel on it; halo
 // values stay frozen during the launch (hybrid GS: Jacobi between tiles, GS inside -- a regular
@@ -203,20 +230,22 @@ k_smooth9(Coarse9 v, const double *__restrict__ b, const double *__restrict__ xi
     if (stopped(st)) return;
     const C9 A{v};
     const int nz = v.nz, nx = v.nx;
-    constexpr int W = kSmTX + 2, H = kSmTZ + 2;
+    constexpr int W = kSmTX + 4, H = kSmTZ + 4;   // 2-cell frame keeps the region aligned to coarse blocks
     __shared__ double sx[H * W];
     const int tiles_x = (nx + kSmTX - 1) / kSmTX, tiles_z = (nz + kSmTZ - 1) / kSmTZ;
     const int tid = threadIdx.x;
     for (long long t = blockIdx.x; t < (long long)tiles_x * tiles_z; t += gridDim.x) {
         const int z0 = (int)(t / tiles_x) * kSmTZ, x0 = (int)(t % tiles_x) * kSmTX;
         for (int k = tid; k < H * W; k += blockDim.x) {
-            const int z = z0 + k / W - 1, xx = x0 + k % W - 1;
+            const int z = z0 + k / W - 2, xx = x0 + k % W - 2;
             double val = 0.0;
-            if (!ZERO_INIT && z >= 0 && z < nz && xx >= 0 && xx < nx) {
+            if (!ZERO_INIT && z >= 0 && z < nz && xx >= 0 && xx < nx)
                 val = xin[(size_t)z * nx + xx];     // never the array this launch writes: other tiles read it
-                if (PROLONG) val += prolong_value(w, e, nzc, nxc, z, xx);
-            }
             sx[k] = val;
+        }
+        if (PROLONG) {
+            __syncthreads();
+            add_prolongation<H, W>(sx, w, e, nzc, nxc, z0 - 2, x0 - 2, nz, nx);
         }
         __syncthreads();
         const int a = tid >> 5, c = tid & 31;
@@ -227,20 +256,20 @@ k_smooth9(Coarse9 v, const double *__restrict__ b, const double *__restrict__ xi
                 const int z = z0 + lz, xx = x0 + lx;
                 if (z < nz && xx < nx) {
                     const size_t i = (size_t)z * nx + xx;
-                    const double *p = &sx[(lz + 1) * W + lx + 1];
+                    double *p = &sx[(lz + 2) * W + lx + 2];
                     double s = b[i];
                     s += A.g(z, xx, 0, -1) * p[-1] + A.g(z, xx, 0, 1) * p[1];
                     s += A.g(z, xx, -1, 0) * p[-W] + A.g(z, xx, 1, 0) * p[W];
                     s += A.g(z, xx, -1, -1) * p[-W - 1] + A.g(z, xx, -1, 1) * p[-W + 1];
                     s += A.g(z, xx, 1, -1) * p[W - 1] + A.g(z, xx, 1, 1) * p[W + 1];
-                    sx[(lz + 1) * W + lx + 1] = s / A.diag(z, xx);
+                    p[0] = s / A.diag(z, xx);
                 }
                 __syncthreads();
             }
         for (int k = tid; k < kSmTZ * kSmTX; k += blockDim.x) {
             const int lz = k / kSmTX, lx = k % kSmTX;
             const int z = z0 + lz, xx = x0 + lx;
-            if (z < nz && xx < nx) xout[(size_t)z * nx + xx] = sx[(lz + 1) * W + lx + 1];
+            if (z < nz && xx < nx) xout[(size_t)z * nx + xx] = sx[(lz + 2) * W + lx + 2];
         }
         __syncthreads();
     }
@@ -346,10 +375,10 @@ k_smooth5_up(Fine5 v, const double *__restrict__ b, const double *__restrict__ x
         const int z0 = (int)(t / tiles_x) * kSmTZ, x0 = (int)(t % tiles_x) * kSmTX;
         for (int k = tid; k < H * W; k += blockDim.x) {
             const int z = z0 + k / W - 2, xx = x0 + k % W - 2;
-            double val = 0.0;
-            if (z >= 0 && z < nz && xx >= 0 && xx < nx) val = xin[(size_t)z * nx + xx] + prolong_value(w, e, nzc, nxc, z, xx);
-            sx[k] = val;
+            sx[k] = (z >= 0 && z < nz && xx >= 0 && xx < nx) ? xin[(size_t)z * nx + xx] : 0.0;
         }
+        __syncthreads();
+        add_prolongation<H, W>(sx, w, e, nzc, nxc, z0 - 2, x0 - 2, nz, nx);
         __syncthreads();
         // black pass over tile + first halo ring
         constexpr int W1 = kSmTX + 2, H1 = kSmTZ + 2;
@@ -539,6 +568,24 @@ double bench_launch_cycle(Solver &s, const std::string &name)
                (const double *)nullptr, f.x, s.nu_coarse, 1, Weights{}, (const double *)nullptr, 0, 0,
                (const PcgState *)s.state);
         return 56.0 * (double)f.n;   // b, C, E, N, NE, NW in; x out (couplings re-read from L1/L2 per sweep)
+    }
+    if (name == "smooth9_l1_up" && s.levels.size() > 2) {
+        Level &f = s.levels[1], &c = s.levels[2];
+        LAUNCH((k_smooth9<false, true>), tile_grid(f.nz, f.nx), 256, 0, s.stream, f.view9(), (const double *)f.b,
+               (const double *)f.x, f.r, s.nu_coarse, 0, f.w, (const double *)c.r, c.nz, c.nx, (const PcgState *)s.state);
+        return 64.0 * (double)f.n + (8.0 + 64.0) * (double)c.n;
+    }
+    if (name == "residual9_l1" && s.levels.size() > 2) {
+        Level &f = s.levels[1];
+        LAUNCH(k_residual9, grid_for(s, f.nz, f.nx, 8), kBlock, 0, s.stream, f.view9(), (const double *)f.b,
+               (const double *)f.x, f.r, s.state);
+        return 64.0 * (double)f.n;   // b, x, S, E, N, NE, NW in; r out
+    }
+    if (name == "restrict1" && s.levels.size() > 2) {
+        Level &f = s.levels[1], &c = s.levels[2];
+        LAUNCH(k_restrict, grid_for(s, c.nz, c.nx, 8), kBlock, 0, s.stream, f.w, (const double *)f.r, f.nz, f.nx,
+               c.b, c.nz, c.nx, s.state);
+        return 8.0 * (double)f.n + 72.0 * (double)c.n;
     }
     if (name == "gs5_first") {
         LAUNCH((k_gs5<GS_FIRST>), g0, kBlock, 0, s.stream, v5, (const double *)s.r, s.z, 0, s.state, 0, part, cnt);

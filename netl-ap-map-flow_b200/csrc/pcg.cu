@@ -200,15 +200,42 @@ int pcg_solve(Solver &s, const BoundaryValues &bv, double rel_tol, int max_iter,
         if (sc) { sc->iterations += 0; sc->converged = 1; sc->rel_residual = 0.0; sc->rel_residual_scaled = 0.0; }
         return 0;
     }
+    auto enqueue_iteration = [&]() {
+        LAUNCH(k_spmv5, g0, kBlock, 0, s.stream, v5, (const double *)s.d, s.q, s.state, part, cnt);
+        LAUNCH(k_update, g1, 256, 0, s.stream, s.x, s.r, (const double *)s.d, (const double *)s.q, n, s.state,
+               part + 4 * kMaxPartials, cnt + 5);
+        mg_vcycle(s, s.r, s.z, s.q, s.state, false);
+        LAUNCH(k_direction, g1, 256, 0, s.stream, s.d, (const double *)s.q, n, (const PcgState *)s.state, 0);
+    };
+#ifndef LCL_CPU_SIM
+    // Every argument of the steady-state iteration is a pointer or size fixed for the solver's lifetime
+    // (the scalars live in s.state on the device), so the ~45 launches are captured once into a CUDA
+    // graph and replayed: small maps are launch bound otherwise.
+    if (!s.iter_graph && !getenv("APM_LCL_NO_GRAPH")) {
+        const long long before = g_launches;
+        cudaGraph_t graph = nullptr;
+        CUDA_CHECK(cudaStreamBeginCapture(s.stream, cudaStreamCaptureModeThreadLocal));
+        enqueue_iteration();
+        CUDA_CHECK(cudaStreamEndCapture(s.stream, &graph));
+        CUDA_CHECK(cudaGraphInstantiate(&s.iter_graph, graph, 0));
+        CUDA_CHECK(cudaGraphDestroy(graph));
+        s.iter_graph_launches = g_launches - before;
+        g_launches = before;
+    }
+#endif
+    auto run_iteration = [&]() {
+#ifndef LCL_CPU_SIM
+        if (s.iter_graph) {
+            CUDA_CHECK(cudaGraphLaunch(s.iter_graph, s.stream));
+            g_launches += s.iter_graph_launches;
+            return;
+        }
+#endif
+        enqueue_iteration();
+    };
     while (!done) {
         while (iters < max_iter) {
-            for (int k = 0; k < check_every && iters < max_iter; k++, iters++) {
-                LAUNCH(k_spmv5, g0, kBlock, 0, s.stream, v5, (const double *)s.d, s.q, s.state, part, cnt);
-                LAUNCH(k_update, g1, 256, 0, s.stream, s.x, s.r, (const double *)s.d, (const double *)s.q, n,
-                       s.state, part + 4 * kMaxPartials, cnt + 5);
-                mg_vcycle(s, s.r, s.z, s.q, s.state, false);
-                LAUNCH(k_direction, g1, 256, 0, s.stream, s.d, (const double *)s.q, n, (const PcgState *)s.state, 0);
-            }
+            for (int k = 0; k < check_every && iters < max_iter; k++, iters++) run_iteration();
             poll_state(s);
             if (debug)
                 fprintf(stderr, "[pcg] it %3d rr/bb %.3e rs/bs %.3e rz %.3e dq %.3e alpha %.3e beta %.3e dx %.3e conv %d fail %d\n",

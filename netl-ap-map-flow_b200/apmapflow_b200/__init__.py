@@ -33,4 +33,4 @@ def set_main_logger_level(level):
     root.setLevel(level)
 
 
-from .run_model import BulkRun, InputFile, estimate_req_RAM, run_model  # noqa: E402,F401
+from . import run_model  # noqa: E402,F401  (the subpackage, like `from apmapflow import run_model`)

@@ -1,0 +1,138 @@
+"""Host-side mirror of the reference's run API (apmapflow_b200.run_model).  The cases follow the
+reference's own unit tests (test/unit/TestRunCore.py, test/unit/TestBulkRun.py) so a user of the
+reference finds the same behaviour; where /root/reference is present the two InputFile
+implementations are also diffed live."""
+import os
+import sys
+
+import pytest
+
+from apmapflow_b200 import run_model as rm
+from apmapflow_b200.run_model import ArgInput, BulkRun, InputFile
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def test_arg_input_parsing():          # TestRunCore.py:23-72
+    arg = ArgInput(";INLET-PRESS:   100  KPA ;CMT-MSG")
+    assert (arg.keyword, arg.value, arg.unit, arg.comment_msg, arg.commented_out) == \
+        ("INLET-PRESS", "100", "KPA", ";CMT-MSG", True)
+    assert arg.line == str(arg)
+    arg.value = 200
+    arg.unit = "PSI"
+    assert (arg.value, arg.unit, arg.commented_out) == ("200", "PSI", False)
+    arg = ArgInput(";OVERWRITE EXISTING FILES")
+    assert arg.value == "OVERWRITE EXISTING FILES" and arg.unit is None
+    arg.value = ("", True)
+    assert arg.line == ";"
+    arg = ArgInput("INLET-PRESS:")
+    assert (arg.value, arg.unit, arg.commented_out) == ("", "", False)
+    arg = ArgInput("")
+    assert arg.value == arg.line
+    assert ArgInput('KEYWORD: "VALUE1 + VALUE2"').value == '"VALUE1 + VALUE2"'
+    arg = ArgInput('TEST: "UNMATCHED QUOTE')
+    assert (arg.value, arg.unit) == ('"UNMATCHED', "QUOTE")
+
+
+def test_input_file_clone_update_formats(tmp_path):      # TestRunCore.py:74-129
+    inp = InputFile(os.path.join(GOLDEN, "test-model-inputs.txt"))
+    assert inp.keys()
+    clone = inp.clone()
+    assert [inp[k].value for k in inp if k] == [clone[k].value for k in clone if k]
+    InputFile(inp)
+    inp.update({"INLET-PRESS": "300", "BAD-ARG": "IN FORMATS"})
+    assert inp["INLET-PRESS"].value == "300"
+    assert inp.filename_format_args["BAD-ARG"] == "IN FORMATS"
+    with pytest.raises(TypeError):
+        inp.update("a", "b", "c")
+    exe = os.path.join(rm.DEFAULT_MODEL_PATH, rm.DEFAULT_MODEL_NAME)
+    inp.add_parameter(";EXE-FILE: " + exe)
+    assert inp["EXE-FILE"].value == exe
+    assert [k for k, v in inp.items() if not v.commented_out] == list(inp.get_uncommented_values().keys())
+    with pytest.raises(KeyError):
+        inp.filename_formats["NONEXISTANT-FILE"] = "NONEXISTANT-FILE-FORMAT"
+        print(inp)
+    del inp.filename_formats["NONEXISTANT-FILE"]
+    inp.filename_formats["input_file"] = "OUT.INP"
+    inp.write_inp_file(alt_path=str(tmp_path))
+    again = InputFile(str(tmp_path / "OUT.INP"))
+    assert again["INLET-PRESS"].value == "300"
+    # a non-existent EXE-FILE falls back to the packaged model (reference :453-491)
+    again["EXE-FILE"] = "does-not-exist.exe"
+    assert again.executable == exe
+
+
+def test_estimate_req_ram():            # TestRunCore.py:131-138
+    path = os.path.join(GOLDEN, "parallel-plate-01vox.txt")
+    assert rm.map_dimensions(path) == (100, 100)
+    ram = rm.estimate_req_RAM([path], 10)
+    assert 0 < ram[0] < 10
+    with pytest.raises(EnvironmentError):
+        rm.estimate_req_RAM([path], 0)
+    assert rm.estimate_req_RAM([path], 0, suppress=True)
+
+
+def test_bulk_run_defaults_and_combinations():          # TestBulkRun.py:21-44
+    inp = InputFile(os.path.join(GOLDEN, "test-model-inputs.txt"))
+    bulk = BulkRun(inp)
+    assert not bulk.input_file_list
+    assert (bulk.num_CPUs, bulk.sys_RAM, bulk.avail_RAM) == (2, 4.0, 3.6)
+    combs = BulkRun._combine_run_params({"param1": [1, 2, 3], "param2": [4, 5], "param3": [6], "param4": None})
+    assert len(combs) == 6
+    assert set(combs[0].keys()) == {"param1", "param2", "param3"}
+    assert set(combs[0].values()) == {6, 4, 1} and set(combs[-1].values()) == {6, 5, 3}
+
+
+def test_bulk_run_check_processes():                    # TestBulkRun.py:46-67
+    class Proc:
+        value = None
+
+        def poll(self):
+            if self.value is None:
+                self.value = 0
+                return None
+            return self.value
+    procs, ram = [Proc()], [0.0]
+    BulkRun._check_processes(procs, ram, retest_delay=0)
+    assert not procs and not ram
+
+
+def test_bulk_run_generate_input_files():               # TestBulkRun.py:69-94 + test-bulk-run.yaml
+    import yaml
+    cfg = yaml.safe_load(open(os.path.join(GOLDEN, "test-bulk-run.yaml")))
+    inp = InputFile(os.path.join(GOLDEN, cfg["initial_input_file"]))
+    inp.add_parameter("APER-MAP: x.txt")
+    inp.add_parameter("SUMMARY-FILE: x"); inp.add_parameter("STAT-FILE: x"); inp.add_parameter("APER-FILE: x")
+    inp.add_parameter("FLOW-FILE: x"); inp.add_parameter("PRESS-FILE: x"); inp.add_parameter("VTK-FILE: x")
+    bulk = BulkRun(inp, **cfg["bulk_run_keyword_args"])
+    bulk.generate_input_files(cfg["default_run_parameters"], cfg["default_file_formats"],
+                              cfg["case_identifier"], cfg["case_parameters"], append=True)
+    # 3 maps x 2 roughness x (3 + 3 + 2 outlet pressures) = 16 simulations
+    assert len(bulk.input_file_list) == 16
+    names = {f.outfile_name for f in bulk.input_file_list}
+    assert "parallel-plate-01vox-RF0.00-500PA-INIT.INP" in names
+    assert "Fracture1ApertureMap-10avg-RF1.00-200PA-INIT.INP" in names
+    assert all(f["INLET-PRESS"].value == "1000" for f in bulk.input_file_list)
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/apmapflow"), reason="reference tree not present (GPU box)")
+def test_input_file_matches_reference_implementation():
+    """Live diff against the reference's own InputFile in the authoring container."""
+    sys.path.insert(0, "/root/reference")
+    try:
+        from apmapflow.run_model.run_model import InputFile as RefInputFile
+    except Exception as exc:       # missing optional deps of the reference
+        pytest.skip("reference package not importable: %s" % exc)
+    finally:
+        sys.path.remove("/root/reference")
+    path = os.path.join(GOLDEN, "coverage_test.inp")
+    ours, ref = InputFile(path), RefInputFile(path)
+    assert list(ours.keys()) == list(ref.keys())
+    for key in ours:
+        assert (ours[key].value, ours[key].unit, ours[key].commented_out, ours[key].line) == \
+               (ref[key].value, ref[key].unit, ref[key].commented_out, ref[key].line), key
+    upd = {"OUTLET-SIDE": "LEFT", "apmap": "fracture-1", "INLET-PRESS": "250"}
+    ours.update(upd)
+    ref.update(upd)
+    assert str(ours) == str(ref)
+    assert ours.filename_format_args == ref.filename_format_args

@@ -1,0 +1,153 @@
+"""File pipeline (csrc/host_io.cpp: .inp parser, unit tables, Fortran-format writers) checked against
+the reference's golden output files.  The numeric core runs through the CPU emulation build of the
+kernels (tests/sim) here; tests/test_gpu_run_file.py repeats it through libapmlcl.so on the GPU."""
+import ctypes as C
+import gzip
+import os
+
+import pytest
+
+from sim import sim_lib
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def golden_text(name):
+    path = os.path.join(GOLDEN, name)
+    if os.path.exists(path + ".gz"):
+        return gzip.open(path + ".gz", "rt").read()
+    return open(path).read()
+
+
+def run(lib, workdir, inp_text, name="case.inp"):
+    path = os.path.join(workdir, name)
+    with open(path, "w") as f:
+        f.write(inp_text)
+    buf = C.create_string_buffer(1 << 22)
+    cwd = os.getcwd()
+    os.chdir(workdir)
+    try:
+        rc = lib.apm_lcl_run_file(name.encode(), 0, buf, len(buf))
+    finally:
+        os.chdir(cwd)
+    return rc, buf.value.decode()
+
+
+def coverage_inp(extra=""):
+    text = open(os.path.join(GOLDEN, "coverage_test.inp")).read()
+    text = text.replace(';APER-MAP:   "(PATH/TO/FILE.*)"', "APER-MAP: " + os.path.join(GOLDEN, "ParallelPlate-1vox.txt"))
+    return text + "\nBAD-INPUT: VALUE\n" + extra
+
+
+def differing_lines(ours, gold):
+    a, b = ours.split("\n"), gold.split("\n")
+    assert len(a) == len(b)
+    return [(i, x, y) for i, (x, y) in enumerate(zip(a, b)) if x.rstrip() != y.rstrip()]
+
+
+def check_against_golden_files(workdir):
+    """What test/fortran/bin/test_model_code_coverage:115-155 diffs, at the precision an f64 solve can
+    reach (the goldens come from the quad build)."""
+    for ours, gold in [("coverage_test_pres.csv", "coverage_test_pres-orig.csv"),
+                       ("coverage_test_aper.csv", "coverage_test_aper-orig.csv"),
+                       ("coverage_test_flow-z.csv", "coverage_test_flow-z-orig.csv"),
+                       ("coverage_test_flow-m.csv", "coverage_test_flow-m-orig.csv")]:
+        assert differing_lines(open(os.path.join(workdir, ours)).read(), golden_text(gold)) == [], ours
+    # stat files: only the APER-MAP path line and 12th-digit rounding of flow-derived values may differ
+    for ours, gold in [("coverage_test_stats.csv", "coverage_test_stats-orig.csv"),
+                       ("coverage_test_stats.yaml", "coverage_test_stats-orig.yaml")]:
+        diff = differing_lines(open(os.path.join(workdir, ours)).read(), golden_text(gold))
+        assert len(diff) <= 3 and diff[0][0] == 0, diff
+        for _, x, y in diff[1:]:
+            assert len(x) == len(y)
+            assert sum(c != d for c, d in zip(x, y)) <= 2, (x, y)
+    # VTK: header, points, APERTURE / PRESSURE / REYNOLDS sections identical; the residual and the
+    # x component of the flow vectors are rounding noise in both builds
+    sec, bad = "header", {}
+    a = open(os.path.join(workdir, "coverage_test_data.vtk")).read().split("\n")
+    b = golden_text("coverage_test_data-orig.vtk").split("\n")
+    assert len(a) == len(b)
+    for x, y in zip(a, b):
+        if y.startswith(("SCALARS", "VECTORS", "POINTS")):
+            sec = y.split()[1]
+        if x.rstrip() != y.rstrip():
+            bad[sec] = bad.get(sec, 0) + 1
+            if sec.startswith("FLOW"):
+                assert x.split()[1:] == y.split()[1:]       # y and z components identical
+    assert set(bad) <= {"NORMALIZED_RESIDUAL[-]", "FLOW[M^3/SEC]"}, bad
+    # log: same line count; solver name / time / residual-noise lines differ
+    diff = differing_lines(open(os.path.join(workdir, "coverage_test_log.txt")).read(), golden_text("coverage_test_log-orig.txt"))
+    allowed = ("USING", "REQUIRED TIME", "MAXIMUM NET FLOW RESIDUAL", "|")
+    assert all(any(k in x for k in allowed) for _, x, _ in diff), diff
+
+
+def test_coverage_case_reproduces_golden_files(tmp_path):
+    rc, out = run(sim_lib.load(), str(tmp_path), coverage_inp(), "coverage_test.inp")
+    assert rc == 0, out
+    assert "USING SUPPLIED INPUT FILE coverage_test.inp" in out and "**** EXITING PROGRAM ****" in out
+    assert "** WARNING: UNRECOGNIZED INPUT: BAD-INPUT: VALUE **" in out
+    check_against_golden_files(str(tmp_path))
+
+
+def small_inp(tmp_path, body, amap="BadApertureMap.txt"):
+    return ("APER-MAP: %s\nSUMMARY-FILE: %s/log.txt\nSTAT-FILE: %s/stat.csv\nAPER-FILE: %s/aper.csv\n"
+            "FLOW-FILE: %s/flow.csv\nPRESS-FILE: %s/pres.csv\nVTK-FILE: %s/data.VTK\nOVERWRITE\n"
+            % ((os.path.join(GOLDEN, amap),) + (str(tmp_path),) * 6)) + body
+
+
+OK_BODY = ("INLET-PRESS: 100 PA\nOUTLET-PRESS: 0 PA\nOUTLET-SIDE: TOP\nFLUID-DENSITY: 1000 KG/M^3\n"
+           "FLUID-VISCOSITY: 1.0 CP\nMAP AVERAGING FACTOR: 1\nVOXEL SIZE: 10 MICRONS\nLOW-MASK: 0.0001\n")
+
+
+@pytest.mark.parametrize("body,amap,pattern", [      # test_model_code_coverage:214-272
+    (OK_BODY, "BadApertureMap.txt", r"FIELD\s*\d+\s*ON THE"),
+    (OK_BODY.replace("FLUID-VISCOSITY: 1.0 CP", "FLUID-VISCOSITY: -1.0 CP"), "parallel-plate-01vox.txt",
+     "ERROR - NONE OR INVAILD VISCOSITY"),
+    (OK_BODY.replace("OUTLET-SIDE: TOP", "OUTLET-SIDE: NOWHERE"), "parallel-plate-01vox.txt",
+     "INVALID OUTLET SIDE ENTERED: NOWHERE"),
+    (OK_BODY + "MAXIMUM MAP DIMENSION: 50\n", "parallel-plate-01vox.txt", "MAXIMUM NUMBER OF HORIZONTAL"),
+    (OK_BODY.replace("INLET-PRESS: 100 PA", "INLET-PRESS: 100"), "parallel-plate-01vox.txt", "INSUFFICIENT"),
+    (OK_BODY.replace("INLET-PRESS: 100 PA", "INLET-PRESS: abc PA"), "parallel-plate-01vox.txt", r"FIELD\s*2\s*ON THE"),
+])
+def test_failure_cases_return_1_with_reference_messages(tmp_path, body, amap, pattern):
+    import re
+    rc, out = run(sim_lib.load(), str(tmp_path), small_inp(tmp_path, body, amap))
+    assert rc == 1
+    assert re.search(pattern, out), out
+
+
+def test_missing_input_and_map_and_overwrite(tmp_path):
+    lib = sim_lib.load()
+    buf = C.create_string_buffer(4096)
+    assert lib.apm_lcl_run_file(b"", 0, buf, 4096) == 1
+    assert b"FATAL ERROR - NO INPUT FILE" in buf.value
+    rc, out = run(lib, str(tmp_path), "OVERWRITE\n" + OK_BODY)
+    assert rc == 1 and "FATAL ERROR - NO APERTURE MAP" in out
+    # second run without OVERWRITE refuses to clobber and removes nothing that existed
+    rc, out = run(lib, str(tmp_path), small_inp(tmp_path, OK_BODY, "parallel-plate-01vox.txt"))
+    assert rc == 0, out
+    assert os.path.exists(tmp_path / "data.vtk")          # extension lower-cased (IO_MODULE.F:169-170)
+    assert os.path.exists(tmp_path / "flow-x.csv") and os.path.exists(tmp_path / "stat.yaml")
+    rc, out = run(lib, str(tmp_path), small_inp(tmp_path, OK_BODY, "parallel-plate-01vox.txt").replace("OVERWRITE\n", ""))
+    assert rc == 1 and 'SPECIFY "OVERWRITE" IN THE' in out
+    assert os.path.exists(tmp_path / "pres.csv")
+
+
+def test_units_and_rate_bc_through_files(tmp_path):
+    body = ("INLET-RATE: 1.0 MM^3/SEC\nOUTLET-PRESS: 1 KPA\nOUTLET-SIDE: RIGHT\nFLUID-DENSITY: 1 G/CM^3\n"
+            "FLUID-VISCOSITY: 1.0 CP\nMAP AVERAGING FACTOR: 10\nVOXEL SIZE: 10 MICRONS\nLOW-MASK: 0.0001\n"
+            "OUTPUT-UNITS: KPA,MM,MM^3/SEC\n")
+    rc, out = run(sim_lib.load(), str(tmp_path), small_inp(tmp_path, body, "parallel-plate-10vox.txt"))
+    assert rc == 0, out
+    assert "FRACTURE FLOW IS RATE CONTROLLED" in out
+    import yaml
+    st = yaml.safe_load(open(tmp_path / "stat.yaml"))
+    assert st["OUTLET RATE"][1] == "MM^3/SEC" and st["OUTLET RATE"][0] == pytest.approx(1.0, rel=1e-6)
+    assert st["OUTLET PRESS"] == [1.0, "KPA"]
+    assert st["INLET PRESS"][0] > 1.0
+    assert st["DENSITY"] == [1.0, "G/CM^3"]
+    # analytic cubic law for a 10-voxel parallel plate gives the inlet pressure
+    w = l = 100 * 10e-6 * 10
+    b = 10 * 10e-6
+    dp = 1e-9 * 12 * 1e-3 * l / (w * b ** 3)
+    assert (st["INLET PRESS"][0] - 1.0) * 1e3 == pytest.approx(dp, rel=1e-6)

@@ -3,6 +3,7 @@
 // The driver is the device-side counterpart of the reference's INITIALIZE_RUN -> FRAC_FLOW ->
 // OUTPUT_DATA sequence (apmapflow/src/APERTURE_MAP_FLOW.F:28-42), restricted to its numeric core.
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 
@@ -77,6 +78,8 @@ static Solver *solver_new(int device, int nx, int nz)
         CUDA_CHECK(cudaMallocHost((void **)&s->scal_host, 64 * sizeof(double)));
         for (auto &e : s->ev) CUDA_CHECK(cudaEventCreate(&e));
         mg_allocate(*s);
+        if (const char *e = getenv("APM_LCL_NU_L1")) s->nu_coarse = atoi(e);     // tuning knobs
+        if (const char *e = getenv("APM_LCL_NU_DEEP")) s->nu_deep = atoi(e);
     } catch (...) {
         solver_free(s);
         throw;

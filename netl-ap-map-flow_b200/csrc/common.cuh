@@ -141,7 +141,7 @@ struct Solver {
     cudaGraphExec_t iter_graph = nullptr;   // one steady-state PCG iteration (spmv, update, V-cycle, direction)
 #endif
     long long iter_graph_launches = 0;
-    int nu_fine = 1, nu_coarse = 2;
+    int nu_fine = 1, nu_coarse = 2, nu_deep = 2;   // sweeps: fine, level 1, levels >= 2
     bool have_solution = false;
     apm_lcl_params last_params{};
     Fine5 view5() const { return Fine5{tx, tz, txl, tzb, nz, nx}; }

@@ -275,106 +275,65 @@ k_smooth9(Coarse9 v, const double *__restrict__ b, const double *__restrict__ xi
     }
 }
 
-// ---- fine-level tiles: faces staged in shared memory so a cell's four conductances, its diagonal and
-// its neighbours come from smem without branches (boundary faces sit where the "missing" neighbour's
-// face would be and multiply a 0 in the x tile).  Rows are walked warp by warp: no div/mod.
-//   sTX[r][j] = right face of cell column (x0 - F - 1 + j), row (z0 - F + r)   (column -1 -> txl)
-//   sTZ[i][c] = top   face of cell row    (z0 - F - 1 + i), column (x0 - F + c) (row -1 -> tzb)
-// with F = frame width of the face region (1 for both kernels).
-template <int F>
-struct FaceTile {
-    static constexpr int R = kSmTZ + 2 * F, C = kSmTX + 2 * F;   // cells covered
-    static constexpr int WX = C + 1, HZ = R + 1;
-    __device__ static __forceinline__ void load(const Fine5 &v, int z0, int x0, double *sTX, double *sTZ)
-    {
-        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
-        const int nz = v.nz, nx = v.nx;
-        for (int r = warp; r < R; r += nwarps) {
-            const int z = z0 - F + r;
-            const bool zin = z >= 0 && z < nz;
-            for (int j = lane; j < WX; j += 32) {
-                const int x = x0 - F - 1 + j;
-                double t = 0.0;
-                if (zin) {
-                    if (x >= 0 && x < nx) t = v.tx[(size_t)z * nx + x];
-                    else if (x == -1) t = v.txl[z];
-                }
-                sTX[r * WX + j] = t;
-            }
-        }
-        for (int i = warp; i < HZ; i += nwarps) {
-            const int z = z0 - F - 1 + i;
-            for (int cc = lane; cc < C; cc += 32) {
-                const int x = x0 - F + cc;
-                double t = 0.0;
-                if (x >= 0 && x < nx) {
-                    if (z >= 0 && z < nz) t = v.tz[(size_t)z * nx + x];
-                    else if (z == -1) t = v.tzb[x];
-                }
-                sTZ[i * C + cc] = t;
-            }
-        }
-    }
-};
-
 // Fine level, down leg: one EXACT red/black sweep from a zero guess in one launch.
 // red = b/diag needs no neighbour, so the red values of the halo ring are recomputed from b and the
-// faces instead of being exchanged; black then sees exactly what a two-pass sweep would see.
+// faces instead of being exchanged; black then sees exactly what the two-pass version saw.
 // ||b||^2 and b^T D^-1 b (= the PCG residual norms) ride along.
 __global__ void __launch_bounds__(256)
 k_smooth5_down(Fine5 v, const double *__restrict__ b, double *__restrict__ x, PcgState *st, int init,
                double *partials, unsigned int *counter)
 {
     if (stopped(st)) return;
-    using FT = FaceTile<1>;
-    constexpr int R = FT::R, C = FT::C, WX = FT::WX;
-    __shared__ double sTX[R * FT::WX], sTZ[FT::HZ * C], sX[R * C];
+    const F5 A{v};
     const int nz = v.nz, nx = v.nx;
+    constexpr int W = kSmTX + 2, H = kSmTZ + 2;
+    __shared__ double sx[H * W];
     const int tiles_x = (nx + kSmTX - 1) / kSmTX, tiles_z = (nz + kSmTZ - 1) / kSmTZ;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tid = threadIdx.x;
     double acc[2] = {0.0, 0.0};
     for (long long t = blockIdx.x; t < (long long)tiles_x * tiles_z; t += gridDim.x) {
         const int z0 = (int)(t / tiles_x) * kSmTZ, x0 = (int)(t % tiles_x) * kSmTX;
-        FT::load(v, z0, x0, sTX, sTZ);
-        __syncthreads();
-        // red cells of tile + ring get b/diag; black cells of the tile keep b for the second pass
-        for (int r = warp; r < R; r += 8) {
-            const int z = z0 - 1 + r;
-            const bool zin = z >= 0 && z < nz, zint = r >= 1 && r <= kSmTZ;
-            for (int cc = lane; cc < C; cc += 32) {
-                const int xx = x0 - 1 + cc;
-                double val = 0.0;
-                if (zin && xx >= 0 && xx < nx) {
-                    const bool interior = zint && cc >= 1 && cc <= kSmTX;
-                    const bool red = ((z + xx) & 1) == 0;
-                    if (red || interior) {
-                        const double bi = b[(size_t)z * nx + xx];
-                        const double dg = (sTX[r * WX + cc] + sTX[r * WX + cc + 1]) + (sTZ[r * C + cc] + sTZ[(r + 1) * C + cc]);
-                        const double inv = 1.0 / dg;
-                        val = red ? bi * inv : bi;
-                        if (interior) { acc[0] += bi * bi; acc[1] += bi * bi * inv; }
-                    }
+        // red pass over tile + halo (colour 0 = (z+x) even); black cells start at 0
+        for (int k = tid; k < H * W; k += blockDim.x) {
+            const int lz = k / W - 1, lx = k % W - 1;
+            const int z = z0 + lz, xx = x0 + lx;
+            double val = 0.0;
+            if (z >= 0 && z < nz && xx >= 0 && xx < nx) {
+                const bool interior = lz >= 0 && lz < kSmTZ && lx >= 0 && lx < kSmTX;
+                const bool red = ((z + xx) & 1) == 0;
+                if (red || interior) {
+                    const double bi = b[(size_t)z * nx + xx];
+                    const double inv = 1.0 / A.diag(z, xx);
+                    if (red) val = bi * inv;
+                    if (interior) { acc[0] += bi * bi; acc[1] += bi * bi * inv; }
                 }
-                sX[r * C + cc] = val;
+            }
+            sx[k] = val;
+        }
+        __syncthreads();
+        // black pass, tile interior only
+        for (int k = tid; k < kSmTZ * kSmTX / 2; k += blockDim.x) {
+            const int lz = k / (kSmTX / 2);
+            const int z = z0 + lz;
+            const int lx = 2 * (k % (kSmTX / 2)) + ((z + 1) & 1);   // (z + x) odd, x0 is even
+            const int xx = x0 + lx;
+            if (z < nz && xx < nx) {
+                const size_t i = (size_t)z * nx + xx;
+                const double *p = &sx[(lz + 1) * W + lx + 1];
+                const double tl = A.left(z, xx), tr = A.right(z, xx), td = A.down(z, xx), tu = A.up(z, xx);
+                double s = b[i];
+                if (xx > 0) s += tl * p[-1];
+                if (xx + 1 < nx) s += tr * p[1];
+                if (z > 0) s += td * p[-W];
+                if (z + 1 < nz) s += tu * p[W];
+                sx[(lz + 1) * W + lx + 1] = s / ((tl + tr) + (td + tu));
             }
         }
         __syncthreads();
-        // black pass (tile interior), then write the tile
-        for (int r = 1 + warp; r <= kSmTZ; r += 8) {
-            const int z = z0 - 1 + r;
-            if (z >= nz) continue;
-            for (int cc = 1 + lane; cc <= kSmTX; cc += 32) {
-                const int xx = x0 - 1 + cc;
-                if (xx >= nx) continue;
-                const double *p = &sX[r * C + cc];
-                double xi = p[0];
-                if (((z + xx) & 1) == 1) {
-                    const double tl = sTX[r * WX + cc], tr = sTX[r * WX + cc + 1], td = sTZ[r * C + cc], tu = sTZ[(r + 1) * C + cc];
-                    const double s = xi + (tl * p[-1] + tr * p[1]) + (td * p[-C] + tu * p[C]);
-                    xi = s / ((tl + tr) + (td + tu));
-                }
-                x[(size_t)z * nx + xx] = xi;
-            }
+        for (int k = tid; k < kSmTZ * kSmTX; k += blockDim.x) {
+            const int lz = k / kSmTX, lx = k % kSmTX;
+            const int z = z0 + lz, xx = x0 + lx;
+            if (z < nz && xx < nx) x[(size_t)z * nx + xx] = sx[(lz + 1) * W + lx + 1];
         }
         __syncthreads();
     }
@@ -398,66 +357,66 @@ k_smooth5_down(Fine5 v, const double *__restrict__ b, double *__restrict__ x, Pc
 }
 
 // Fine level, up leg: x += P e, then one EXACT black/red sweep, and b.x (= r.z of PCG) in one launch.
-// The tile carries a 2-cell frame of x + P e so the black cells of the first ring can be updated
-// redundantly and the red cells of the tile see exactly what a two-pass sweep would see.
+// The tile carries a 2-cell halo of x + P e so the black cells of the first halo ring can be updated
+// redundantly and the red cells of the tile see exactly what the two-pass version saw.
 __global__ void __launch_bounds__(256)
 k_smooth5_up(Fine5 v, const double *__restrict__ b, const double *__restrict__ xin, double *__restrict__ xout, Weights w,
              const double *__restrict__ e, int nzc, int nxc, PcgState *st, int init, double *partials, unsigned int *counter)
 {
     if (stopped(st)) return;
-    using FT = FaceTile<1>;
-    constexpr int R = FT::R, C = FT::C, WX = FT::WX;       // face region: tile + 1 ring
-    constexpr int W = kSmTX + 4, H = kSmTZ + 4;            // x region: tile + 2 rings
-    __shared__ double sTX[R * FT::WX], sTZ[FT::HZ * C], sx[H * W];
+    const F5 A{v};
     const int nz = v.nz, nx = v.nx;
+    constexpr int W = kSmTX + 4, H = kSmTZ + 4;
+    __shared__ double sx[H * W];
     const int tiles_x = (nx + kSmTX - 1) / kSmTX, tiles_z = (nz + kSmTZ - 1) / kSmTZ;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tid = threadIdx.x;
     double acc[2] = {0.0, 0.0};
     for (long long t = blockIdx.x; t < (long long)tiles_x * tiles_z; t += gridDim.x) {
         const int z0 = (int)(t / tiles_x) * kSmTZ, x0 = (int)(t % tiles_x) * kSmTX;
-        FT::load(v, z0, x0, sTX, sTZ);
-        for (int r = warp; r < H; r += 8) {
-            const int z = z0 - 2 + r;
-            const bool zin = z >= 0 && z < nz;
-            for (int cc = lane; cc < W; cc += 32) {
-                const int xx = x0 - 2 + cc;
-                sx[r * W + cc] = (zin && xx >= 0 && xx < nx) ? xin[(size_t)z * nx + xx] : 0.0;
-            }
+        for (int k = tid; k < H * W; k += blockDim.x) {
+            const int z = z0 + k / W - 2, xx = x0 + k % W - 2;
+            sx[k] = (z >= 0 && z < nz && xx >= 0 && xx < nx) ? xin[(size_t)z * nx + xx] : 0.0;
         }
         __syncthreads();
         add_prolongation<H, W>(sx, w, e, nzc, nxc, z0 - 2, x0 - 2, nz, nx);
         __syncthreads();
-        // black pass over tile + first ring (face-region coordinates r, cc; x-region is shifted by one)
-        for (int r = warp; r < R; r += 8) {
-            const int z = z0 - 1 + r;
-            if (z < 0 || z >= nz) continue;
-            for (int cc = lane; cc < C; cc += 32) {
-                const int xx = x0 - 1 + cc;
-                if (xx < 0 || xx >= nx || ((z + xx) & 1) == 0) continue;
-                double *p = &sx[(r + 1) * W + cc + 1];
-                const double tl = sTX[r * WX + cc], tr = sTX[r * WX + cc + 1], td = sTZ[r * C + cc], tu = sTZ[(r + 1) * C + cc];
-                const double s = b[(size_t)z * nx + xx] + (tl * p[-1] + tr * p[1]) + (td * p[-W] + tu * p[W]);
-                p[0] = s / ((tl + tr) + (td + tu));
+        // black pass over tile + first halo ring
+        constexpr int W1 = kSmTX + 2, H1 = kSmTZ + 2;
+        for (int k = tid; k < H1 * W1; k += blockDim.x) {
+            const int lz = k / W1 - 1, lx = k % W1 - 1;
+            const int z = z0 + lz, xx = x0 + lx;
+            if (z >= 0 && z < nz && xx >= 0 && xx < nx && ((z + xx) & 1) == 1) {
+                const size_t i = (size_t)z * nx + xx;
+                const double *p = &sx[(lz + 2) * W + lx + 2];
+                const double tl = A.left(z, xx), tr = A.right(z, xx), td = A.down(z, xx), tu = A.up(z, xx);
+                double s = b[i];
+                if (xx > 0) s += tl * p[-1];
+                if (xx + 1 < nx) s += tr * p[1];
+                if (z > 0) s += td * p[-W];
+                if (z + 1 < nz) s += tu * p[W];
+                sx[(lz + 2) * W + lx + 2] = s / ((tl + tr) + (td + tu));
             }
         }
         __syncthreads();
-        // red pass over the tile, dot product over every tile cell, write out of place
-        for (int r = 1 + warp; r <= kSmTZ; r += 8) {
-            const int z = z0 - 1 + r;
-            if (z >= nz) continue;
-            for (int cc = 1 + lane; cc <= kSmTX; cc += 32) {
-                const int xx = x0 - 1 + cc;
-                if (xx >= nx) continue;
+        // red pass, tile interior, and the dot product over every interior cell
+        for (int k = tid; k < kSmTZ * kSmTX; k += blockDim.x) {
+            const int lz = k / kSmTX, lx = k % kSmTX;
+            const int z = z0 + lz, xx = x0 + lx;
+            if (z < nz && xx < nx) {
                 const size_t i = (size_t)z * nx + xx;
-                const double *p = &sx[(r + 1) * W + cc + 1];
+                const double *p = &sx[(lz + 2) * W + lx + 2];
                 const double bi = b[i];
                 double xi = p[0];
                 if (((z + xx) & 1) == 0) {
-                    const double tl = sTX[r * WX + cc], tr = sTX[r * WX + cc + 1], td = sTZ[r * C + cc], tu = sTZ[(r + 1) * C + cc];
-                    const double s = bi + (tl * p[-1] + tr * p[1]) + (td * p[-W] + tu * p[W]);
+                    const double tl = A.left(z, xx), tr = A.right(z, xx), td = A.down(z, xx), tu = A.up(z, xx);
+                    double s = bi;
+                    if (xx > 0) s += tl * p[-1];
+                    if (xx + 1 < nx) s += tr * p[1];
+                    if (z > 0) s += td * p[-W];
+                    if (z + 1 < nz) s += tu * p[W];
                     xi = s / ((tl + tr) + (td + tu));
                 }
-                xout[i] = xi;       // out of place: neighbouring tiles still read xin for their frames
+                xout[i] = xi;       // out of place: neighbouring tiles still read xin for their halos
                 acc[0] += bi * xi;
             }
         }

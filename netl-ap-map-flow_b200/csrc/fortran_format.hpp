@@ -86,8 +86,8 @@ inline std::string G(int w, int d, double x)
 // Iw.m
 inline std::string I(int w, int m, long long v)
 {
-    char buf[64];
-    snprintf(buf, sizeof buf, "%0*lld", m > 0 ? m : 1, v < 0 ? -v : v);
+    char buf[96];
+    snprintf(buf, sizeof buf, "%0*lld", m > 0 ? (m < 40 ? m : 40) : 1, v < 0 ? -v : v);
     std::string s = std::string(v < 0 ? "-" : "") + buf;
     if (w == 0) return s;
     if ((int)s.size() > w) return stars(w);

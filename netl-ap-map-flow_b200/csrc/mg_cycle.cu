@@ -458,6 +458,48 @@ k_restrict(Weights w, const double *__restrict__ r, int nz, int nx, double *__re
     }
 }
 
+// Fine level: residual and restriction in one pass, bc = P^T (b - A x), without storing the residual.
+// After the red/black pre-smoothing sweep the residual of every BLACK cell is zero (they were solved
+// last), and in the 3x3 neighbourhood of a coarse point (even z, even x) the four edge cells are
+// exactly the black ones: only the coarse cell itself and its four diagonal (centre-type) cells
+// contribute.  Their residuals are evaluated in difference form from x and the faces.
+__device__ __forceinline__ double residual5_at(const F5 &A, const double *__restrict__ b, const double *__restrict__ x,
+                                               int z, int xx, int nz, int nx)
+{
+    const size_t i = (size_t)z * nx + xx;
+    const double xi = x[i];
+    double s = b[i];
+    s -= A.left(z, xx) * (xi - (xx > 0 ? x[i - 1] : 0.0));
+    s -= A.right(z, xx) * (xi - (xx + 1 < nx ? x[i + 1] : 0.0));
+    s -= A.down(z, xx) * (xi - (z > 0 ? x[i - nx] : 0.0));
+    s -= A.up(z, xx) * (xi - (z + 1 < nz ? x[i + nx] : 0.0));
+    return s;
+}
+
+__global__ void __launch_bounds__(kBlock)
+k_restrict_residual5(Fine5 v, Weights w, const double *__restrict__ b, const double *__restrict__ x,
+                     double *__restrict__ bc, int nzc, int nxc, const PcgState *st)
+{
+    if (stopped(st)) return;
+    const F5 A{v};
+    const int nz = v.nz, nx = v.nx;
+    const Tiles tiles(nzc, nxc);
+    for (long long t = blockIdx.x; t < tiles.ntiles; t += gridDim.x) {
+        int Z, X;
+        tiles.cell(t, Z, X);
+        if (Z >= nzc || X >= nxc) continue;
+        const int z = 2 * Z, xx = 2 * X;
+        const size_t bk = (size_t)Z * nxc + X;
+        const bool xm = X > 0, xp = xx + 1 < nx, zm = Z > 0, zp = z + 1 < nz;
+        double s = residual5_at(A, b, x, z, xx, nz, nx);
+        if (zp && xp) s += w.csw[bk] * residual5_at(A, b, x, z + 1, xx + 1, nz, nx);
+        if (zp && xm) s += w.cse[bk - 1] * residual5_at(A, b, x, z + 1, xx - 1, nz, nx);
+        if (zm && xp) s += w.cnw[bk - nxc] * residual5_at(A, b, x, z - 1, xx + 1, nz, nx);
+        if (zm && xm) s += w.cne[bk - nxc - 1] * residual5_at(A, b, x, z - 1, xx - 1, nz, nx);
+        bc[bk] = s;
+    }
+}
+
 // x += P e : thread per coarse block writes its (up to) four fine points
 __global__ void __launch_bounds__(kBlock)
 k_prolong_add(Weights w, const double *__restrict__ e, int nzc, int nxc, double *__restrict__ x, int nz, int nx,
@@ -569,6 +611,12 @@ double bench_launch_cycle(Solver &s, const std::string &name)
                (const PcgState *)s.state);
         return 56.0 * (double)f.n;   // b, C, E, N, NE, NW in; x out (couplings re-read from L1/L2 per sweep)
     }
+    if (name == "restrict_residual0" && s.levels.size() > 1 && s.levels[0].w.hw) {
+        Level &c = s.levels[1];
+        LAUNCH(k_restrict_residual5, grid_for(s, c.nz, c.nx, 8), kBlock, 0, s.stream, v5, s.levels[0].w,
+               (const double *)s.r, (const double *)s.z, c.b, c.nz, c.nx, (const PcgState *)s.state);
+        return 32.0 * n + (8.0 + 32.0) * (double)c.n;   // b, x, tx, tz in; 4 weights in + coarse rhs out
+    }
     if (name == "smooth9_l1_up" && s.levels.size() > 2) {
         Level &f = s.levels[1], &c = s.levels[2];
         LAUNCH((k_smooth9<false, true>), tile_grid(f.nz, f.nx), 256, 0, s.stream, f.view9(), (const double *)f.b,
@@ -666,11 +714,10 @@ void mg_vcycle(Solver &s, const double *r, double *ztmp, double *zout, PcgState 
     // residual it held has been restricted by then).  Fine level: ztmp after the down leg, zout final;
     // zout doubles as the fine residual buffer in between.
     LAUNCH(k_smooth5_down, tile_grid(s.nz, s.nx), 256, 0, s.stream, v5, r, ztmp, st, init, part, cnt);
-    LAUNCH(k_residual5, g0, kBlock, 0, s.stream, v5, r, (const double *)ztmp, zout, st);
     {
         Level &c = s.levels[1];
-        LAUNCH(k_restrict, grid_for(s, c.nz, c.nx, 8), kBlock, 0, s.stream, s.levels[0].w, (const double *)zout,
-               s.nz, s.nx, c.b, c.nz, c.nx, st);
+        LAUNCH(k_restrict_residual5, grid_for(s, c.nz, c.nx, 8), kBlock, 0, s.stream, v5, s.levels[0].w, r,
+               (const double *)ztmp, c.b, c.nz, c.nx, (const PcgState *)st);
     }
     const Weights now{};
     for (size_t l = 1; l + 1 < nlev; l++) {

@@ -114,6 +114,8 @@ inline long long __shfl_xor_sync(unsigned, long long v, int o)
     cusim_warp_barrier(warp, lanes);
     return r;
 }
+struct alignas(16) double2 { double x, y; };
+inline double2 make_double2(double a, double b) { return double2{a, b}; }
 inline double __ldcg(const double *p) { return *p; }
 inline void __threadfence() {}
 inline unsigned atomicInc(unsigned *a, unsigned lim)

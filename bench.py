@@ -134,12 +134,26 @@ def cpu_baseline(sample_n, seed=0, contact=0.2):
                       % (sample_n, sample_n, wall, sc["solve_seconds"])}, a, sc
 
 
-def _ref_worker(args):
+_REF_MAPS = {}
+
+
+def _ref_prepare(args):
+    """Generate (untimed) and keep the worker's map: pool workers are pinned to one task each."""
     n, seed = args
     import torch
     torch.set_num_threads(1)
     from oracle import oracle_binding as ob
-    a = synth_map_torch(n, seed, "cpu").numpy()
+    ob.load()
+    _REF_MAPS[(n, seed)] = synth_map_torch(n, seed, "cpu").numpy()
+    return os.getpid()
+
+
+def _ref_worker(args):
+    n, seed = args
+    from oracle import oracle_binding as ob
+    a = _REF_MAPS.get((n, seed))
+    if a is None:                      # the task landed on another worker than its prepare step
+        a = synth_map_torch(n, seed, "cpu").numpy()
     t0 = time.time()
     ob.solve(synth_params(), a, want=("pressure",))
     return time.time() - t0
@@ -160,10 +174,13 @@ def run_reference(args):
     ctx = mp.get_context("spawn")
     with ctx.Pool(cores) as pool:
         for step in range(args.warmup + args.steps):
+            tasks = [(n, 1000 * step + k) for k in range(cores)]
+            pool.map(_ref_prepare, tasks, chunksize=1)          # synthetic inputs: not timed
             t0 = time.time()
-            pool.map(_ref_worker, [(n, 1000 * step + k) for k in range(cores)])
+            per_task = pool.map(_ref_worker, tasks, chunksize=1)
+            wall = time.time() - t0
             if step >= args.warmup:
-                times.append(time.time() - t0)
+                times.append(max(wall, max(per_task)))
     ms = 1e3 * sum(times) / len(times)
     value = cores * n * n / (ms * 1e-3) / 1e6
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
@@ -309,8 +326,15 @@ def main():
         kern[name] = {"ms": ms, "GBps": nbytes / ms / 1e6, "frac": nbytes / ms / 1e6 / peak,
                       "bytes_per_cell": nbytes / cells, "launches_per_iter": per_iter[name]}
     dom = max((k for k in kern if k != "vcycle"), key=lambda k: kern[k]["ms"] * kern[k]["launches_per_iter"])
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")
+    if os.path.exists(tpath):
+        tj = json.load(open(tpath))
+        if tj.get("size") == n and dom in tj["kernels"]:
+            traffic = tj["kernels"][dom]["dram_read_bytes"] + tj["kernels"][dom]["dram_write_bytes"]
     roofline = {"bound": "hbm", "kernel": dom, "achieved": kern[dom]["GBps"], "peak": peak, "unit": "GB/s",
-                "frac": kern[dom]["frac"], "traffic": None, "peak_source": peak_src, "kernels": kern}
+                "frac": kern[dom]["frac"], "traffic": traffic,
+                "algorithmic_bytes": kern[dom]["bytes_per_cell"] * cells, "peak_source": peak_src, "kernels": kern}
 
     cpu = None
     if not args.no_cpu_baseline:

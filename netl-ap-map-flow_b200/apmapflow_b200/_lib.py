@@ -90,7 +90,7 @@ def load():
         raise OSError(
             "libapmlcl.so not found at %s -- build it with `python -c 'import __graft_entry__ as g; "
             "g.build()'` (nvcc, sm_100a). There is no CPU fallback." % LIB_PATH)
-    lib = C.CDLL(LIB_PATH, mode=C.RTLD_GLOBAL)
+    lib = C.CDLL(LIB_PATH)
     _lib = bind(lib)
     return _lib
 

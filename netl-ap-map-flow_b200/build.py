@@ -60,7 +60,8 @@ def build(force=False, verbose=False):
     if failed:
         raise RuntimeError("nvcc failed")
     if force or procs or not os.path.exists(LIB):
-        cmd = [NVCC] + ARCH + ["-shared", "-o", LIB] + objs + ["-cudart", "static", "-ccbin", "/usr/bin/g++"]
+        cmd = [NVCC] + ARCH + ["-shared", "-Xlinker", "-Bsymbolic", "-o", LIB] + objs + \
+              ["-cudart", "static", "-ccbin", "/usr/bin/g++"]
         subprocess.check_call(cmd)
     main_cpp = os.path.join(CSRC, "main.cpp")
     if os.path.exists(main_cpp) and (force or _newer(EXE, [main_cpp, LIB])):

@@ -31,7 +31,7 @@ def build(force=False):
         procs.append(subprocess.Popen(cmd))
     if any(p.wait() != 0 for p in procs):
         raise RuntimeError("sim build failed")
-    subprocess.check_call(["/usr/bin/g++", "-shared", "-o", LIB] + objs)
+    subprocess.check_call(["/usr/bin/g++", "-shared", "-Wl,-Bsymbolic", "-o", LIB] + objs)
     return LIB
 
 

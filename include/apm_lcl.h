@@ -117,6 +117,16 @@ APM_LCL_API int apm_lcl_solver_solve(apm_lcl_solver *s, const apm_lcl_params *p,
 APM_LCL_API int apm_lcl_solve(const apm_lcl_params *p, const double *aperture, int nx, int nz, int device,
                   apm_lcl_fields *out, apm_lcl_scalars *sc);
 
+/* Many independent cases of one map size on one device (the tensor-level counterpart of
+ * BulkRun, apmapflow/run_model/bulk_run.py:107-128: independent simulations, no exchange between
+ * them).  Case k uses params[k], apertures[k] and writes outs[k] / scalars[k]; one solver object is
+ * reused, so allocations, the CUDA graph and the multigrid storage are paid once.  Returns the number
+ * of failed cases (0 = all good); a failed case has scalars[k].converged == 0 and the last message in
+ * apm_lcl_last_error().  Shard the case list over GPUs by calling this once per device from one
+ * thread/process per device (apmapflow_b200.lcl.bulk_solve does that). */
+APM_LCL_API int apm_lcl_bulk_solve(int device, int nx, int nz, int n_cases, const apm_lcl_params *params,
+                                   const double *const *apertures, apm_lcl_fields *outs, apm_lcl_scalars *scalars);
+
 /* File-level entry point: what `apm-lcl-model.exe file.inp` does (APERTURE_MAP_FLOW.F:1-51).  Reads the
  * initialization file (OPEN_IO IO_MODULE.F:51, READ_MASTER APERTURE_MAP_FLOW.F:191), the aperture map
  * (READ_DATA_MAP MAP_MODULE.F:18), runs the hot path on `device` and writes the log, stat (csv+yaml),

@@ -75,7 +75,7 @@ EXPORTS = (
     "apm_lcl_version", "apm_lcl_last_error", "apm_lcl_last_launch_count", "apm_lcl_default_params",
     "apm_lcl_solver_create", "apm_lcl_solver_destroy", "apm_lcl_solver_solve", "apm_lcl_solve",
     "apm_lcl_conductance", "apm_lcl_solver_device_field", "apm_lcl_solver_time_kernel",
-    "apm_lcl_run_file",
+    "apm_lcl_run_file", "apm_lcl_bulk_solve",
 )
 
 _lib = None
@@ -114,6 +114,9 @@ def bind(lib):
                                                 C.POINTER(C.c_size_t)]
     lib.apm_lcl_solver_time_kernel.argtypes = [C.c_void_p, C.c_char_p, C.c_int,
                                                C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    lib.apm_lcl_bulk_solve.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(Params),
+                                       C.POINTER(C.c_void_p), C.POINTER(Fields), C.POINTER(Scalars)]
+    lib.apm_lcl_bulk_solve.restype = C.c_int
     lib.apm_lcl_run_file.argtypes = [C.c_char_p, C.c_int, C.c_char_p, C.c_size_t]
     lib.apm_lcl_run_file.restype = C.c_int
     return lib

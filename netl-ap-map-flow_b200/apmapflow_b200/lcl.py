@@ -100,3 +100,53 @@ def conductance(params, aperture, device=0, lib=None):
     if rc != 0:
         raise _lib.LclError((lib.apm_lcl_last_error() or b"").decode())
     return width, trx, trz, sc.as_dict()
+
+
+def bulk_solve(cases, devices=(0,), fields=("pressure",), lib=None):
+    """Independent cases sharded over GPUs, one host thread per device (ctypes drops the GIL).
+
+    ``cases`` is a list of ``(Params, aperture[nz, nx])`` with one common map shape (host numpy
+    arrays).  Device ``d`` of ``devices`` gets the contiguous block ``dist.shard(cases, d, len(devices))``
+    -- no exchange between cases, exactly like the reference's BulkRun.  Returns a list of
+    ``(dict of arrays, dict of scalars)`` in case order."""
+    import threading
+    from . import dist
+    lib = lib if lib is not None else _lib.load()
+    if not cases:
+        return []
+    nz, nx = cases[0][1].shape
+    results = [None] * len(cases)
+    index = list(range(len(cases)))
+    errors = []
+
+    def work(slot, device):
+        mine = dist.shard(index, slot, len(devices))
+        if not mine:
+            return
+        n = len(mine)
+        params = (Params * n)(*[cases[k][0] for k in mine])
+        maps = [np.ascontiguousarray(cases[k][1], dtype=np.float64) for k in mine]
+        assert all(m.shape == (nz, nx) for m in maps)
+        ptrs = (C.c_void_p * n)(*[m.ctypes.data for m in maps])
+        outs = (Fields * n)()
+        arrays = []
+        for j in range(n):
+            arr = {name: np.empty((nz, nx)) for name in fields}
+            for name, a in arr.items():
+                setattr(outs[j], name, a.ctypes.data)
+            arrays.append(arr)
+        scal = (Scalars * n)()
+        failed = lib.apm_lcl_bulk_solve(int(device), nx, nz, n, params, ptrs, outs, scal)
+        if failed:
+            errors.append((device, failed, (lib.apm_lcl_last_error() or b"").decode()))
+        for j, k in enumerate(mine):
+            results[k] = (arrays[j], scal[j].as_dict())
+
+    threads = [threading.Thread(target=work, args=(slot, dev)) for slot, dev in enumerate(devices)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    if errors:
+        raise _lib.LclError("bulk_solve: %s" % errors)
+    return results

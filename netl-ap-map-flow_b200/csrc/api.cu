@@ -348,6 +348,35 @@ int apm_lcl_solve(const apm_lcl_params *p, const double *aperture, int nx, int n
     return rc;
 }
 
+int apm_lcl_bulk_solve(int device, int nx, int nz, int n_cases, const apm_lcl_params *params,
+                       const double *const *apertures, apm_lcl_fields *outs, apm_lcl_scalars *scalars)
+{
+    if (n_cases <= 0) return 0;
+    if (!params || !apertures) {
+        g_last_error = "params / apertures pointer is NULL";
+        return n_cases;
+    }
+    apm_lcl_solver *h = nullptr;
+    if (apm_lcl_solver_create(&h, device, nx, nz)) return n_cases;
+    int failed = 0;
+    std::string first_error;
+    long long launches = 0;
+    for (int k = 0; k < n_cases; k++) {
+        apm_lcl_scalars local{};
+        apm_lcl_scalars *sc = scalars ? &scalars[k] : &local;
+        if (apm_lcl_solver_solve(h, &params[k], apertures[k], outs ? &outs[k] : nullptr, sc)) {
+            failed++;
+            sc->converged = 0;
+            if (first_error.empty()) first_error = g_last_error;
+        }
+        launches += g_launches;
+    }
+    apm_lcl_solver_destroy(h);
+    g_launches = launches;
+    g_last_error = first_error;
+    return failed;
+}
+
 int apm_lcl_conductance(const apm_lcl_params *p, const double *aperture, int nx, int nz, int device, double *width,
                         double *trx, double *trz, apm_lcl_scalars *sc)
 {

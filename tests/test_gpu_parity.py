@@ -163,3 +163,18 @@ def test_torch_cuda_tensor_io_matches_host_io():
         assert f_dev[k].is_cuda
         assert np.array_equal(f_dev[k].cpu().numpy(), f_host[k], equal_nan=True)
     assert s_dev["flow"] == s_host["flow"]
+
+
+def test_bulk_solve_matches_single_solves():
+    """BASELINE config 5 in miniature: (map, outlet pressure) sweep through apm_lcl_bulk_solve."""
+    maps = [synth_aperture(96, 128, seed=k, sigma_c=4, contact=0.1, sigma_k=6) for k in range(3)]
+    cases = [(synth_params(outlet_pressure=p_out), m) for m in maps for p_out in (0.0, 250.0, 937.5)]
+    res = lcl.bulk_solve(cases, devices=(0,), fields=("pressure", "flow_z"))
+    assert len(res) == 9
+    for (p, m), (arr, sc) in zip(cases, res):
+        f, s = lcl.lcl_solve(p, m, fields=("pressure", "flow_z"))
+        assert sc["converged"] == 1 and sc["outlet_pressure"] == p.outlet_pressure
+        assert np.array_equal(arr["pressure"], f["pressure"]) and sc["flow"] == s["flow"]
+    # affine in the boundary pressures: flow scales with (P_in - P_out) on the same map
+    q0, q1 = res[0][1]["flow"], res[1][1]["flow"]
+    assert q1 / q0 == pytest.approx(750.0 / 1000.0, rel=1e-6)

@@ -21,6 +21,7 @@
 #include <functional>
 #include <sstream>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include <sys/stat.h>
@@ -63,6 +64,58 @@ std::string fixed(const std::string &s, size_t n)
     std::string r = s.substr(0, std::min(n, s.size()));
     r.resize(n, ' ');
     return r;
+}
+
+// ------------------------------------------------------------------------------------------
+// Host-side parallelism for the ASCII pipeline (once the solve takes milliseconds,
+// text I/O is the run time).  Rows are formatted by a pool of threads in waves and written in order, so
+// the files are byte-identical to the sequential writer.
+unsigned io_threads()
+{
+    unsigned n = std::thread::hardware_concurrency();
+    if (n == 0) n = 4;
+    return n > 32 ? 32 : n;
+}
+
+template <class Fn>   // fn(row, std::string &out) appends the text of one row
+void write_rows_parallel(FILE *f, long long nrows, Fn fn)
+{
+    const unsigned T = io_threads();
+    const long long per_task = 32;
+    if (nrows <= per_task * 2 || T == 1) {
+        std::string buf;
+        for (long long r = 0; r < nrows; r++) {
+            fn(r, buf);
+            if (buf.size() > (1u << 20)) { fwrite(buf.data(), 1, buf.size(), f); buf.clear(); }
+        }
+        fwrite(buf.data(), 1, buf.size(), f);
+        return;
+    }
+    std::vector<std::string> bufs(T);
+    for (long long wave = 0; wave < nrows; wave += per_task * T) {
+        std::vector<std::thread> pool;
+        for (unsigned t = 0; t < T; t++) {
+            const long long b = wave + per_task * t, e = std::min(nrows, b + per_task);
+            if (b >= e) break;
+            pool.emplace_back([&, t, b, e]() {
+                bufs[t].clear();
+                for (long long r = b; r < e; r++) fn(r, bufs[t]);
+            });
+        }
+        for (auto &th : pool) th.join();
+        for (size_t t = 0; t < pool.size(); t++) fwrite(bufs[t].data(), 1, bufs[t].size(), f);
+    }
+}
+
+template <class Fn>   // fn(begin, end, slot) over [0, n) split into `slots` contiguous parts
+void parallel_ranges(long long n, unsigned slots, Fn fn)
+{
+    std::vector<std::thread> pool;
+    for (unsigned t = 0; t < slots; t++) {
+        const long long b = n * t / slots, e = n * (t + 1) / slots;
+        pool.emplace_back([&, b, e, t]() { fn(b, e, t); });
+    }
+    for (auto &th : pool) th.join();
 }
 
 // ------------------------------------------------------------------------------------------
@@ -527,35 +580,112 @@ bool read_master(Run &r, std::ifstream &in)
     return true;
 }
 
-// READ_DATA_MAP, MAP_MODULE.F:18-85
+// One record of a data map under LNPROC's rules (no quotes in the file): fields end at blanks / '='
+// (no empty fields) or ',' / TAB (two in a row make an empty field), ';' starts a comment.
+// Returns the number of fields; *bad = 1-based index of a field that is not a number (0 = none).
+int parse_map_line(const char *p, const char *end, int maxfld, std::vector<double> &vals, int *bad)
+{
+    vals.clear();
+    *bad = 0;
+    int state = 0;   // 1 inside a field, 0 after ',' / TAB, -1 after a blank or '='
+    const char *fs = nullptr;
+    int nfld = 0;
+    auto close = [&](const char *fe) {
+        char tmp[128];
+        size_t len = (size_t)(fe - fs);
+        if (len >= sizeof tmp) len = sizeof tmp - 1;
+        memcpy(tmp, fs, len);
+        tmp[len] = '\0';
+        double v;
+        if (!read_real(tmp, v) && !*bad) *bad = nfld;
+        vals.push_back(v);
+    };
+    for (; p <= end; p++) {
+        const char c = p < end ? *p : ' ';
+        if (c == ';') { if (state == 1) close(p); state = -1; break; }
+        if (c == ' ' || c == '=' || c == '\r') {
+            if (state == 1) { close(p); state = -1; }
+        } else if (c == ',' || c == '\t') {
+            if (state == 1) { close(p); state = 0; }
+            else if (state == 0) {
+                if (nfld == maxfld) return nfld;
+                nfld++;
+                vals.push_back(0.0);
+                if (!*bad) *bad = nfld;          // a blank field cannot be read as a number
+            } else state = 0;
+        } else if (state != 1) {
+            if (nfld == maxfld) return nfld;
+            nfld++;
+            fs = p;
+            state = 1;
+        }
+    }
+    return nfld;
+}
+
+// READ_DATA_MAP, MAP_MODULE.F:18-85.  The whole file is read once and its records are parsed by a pool
+// of threads (records are independent when the file has no double quotes; otherwise the sequential
+// LNPROC reader with its carried-over quote state is used).
 bool read_data_map(Run &r)
 {
-    std::ifstream in(r.apm_file);
+    std::ifstream in(r.apm_file, std::ios::binary);
     if (!in) {
         r.to_stdout("IO ERROR: " + std::to_string(errno) + " ATTEMPTING TO OPEN: " + r.apm_file);
         return false;
     }
-    LineReader lr(in);
-    std::vector<std::string> f;
-    std::string rec;
+    std::string text((std::istreambuf_iterator<char>(in)), std::istreambuf_iterator<char>());
+    in.close();
     std::vector<std::vector<double>> rows;
-    int n, nx = 0;
-    while ((n = lr.next(f, rec, r.maxdim + 1)) > 0) {
-        if (n > r.maxdim) {
-            r.message(" ERROR - MAXIMUM NUMBER OF HORIZONTAL CELLS IS " + std::to_string(r.maxdim));
-            return false;
+    int nx = 0;
+    auto horizontal = [&]() { r.message(" ERROR - MAXIMUM NUMBER OF HORIZONTAL CELLS IS " + std::to_string(r.maxdim)); return false; };
+    auto vertical = [&]() { r.message(" ERROR - MAXIMUM NUMBER OF VERTICAL CELLS IS " + std::to_string(r.maxdim)); return false; };
+    if (text.find('"') != std::string::npos) {
+        std::istringstream iss(text);
+        LineReader lr(iss);
+        std::vector<std::string> f;
+        std::string rec;
+        int n;
+        while ((n = lr.next(f, rec, r.maxdim + 1)) > 0) {
+            if (n > r.maxdim) return horizontal();
+            if ((int)rows.size() + 1 > r.maxdim) return vertical();
+            rows.emplace_back((size_t)n);
+            for (int k = 0; k < n; k++)
+                if (!read_real(f[k], rows.back()[k])) {
+                    field_error(r, "APERTURE MAP", k + 1, "LINE - " + fixed(rec, 70) + "...");
+                    return false;
+                }
+            nx = n;
         }
-        if ((int)rows.size() + 1 > r.maxdim) {
-            r.message(" ERROR - MAXIMUM NUMBER OF VERTICAL CELLS IS " + std::to_string(r.maxdim));
-            return false;
+    } else {
+        std::vector<std::pair<size_t, size_t>> lines;   // [begin, end) of every record
+        for (size_t b = 0; b < text.size();) {
+            size_t e = text.find('\n', b);
+            if (e == std::string::npos) e = text.size();
+            lines.emplace_back(b, e);
+            b = e + 1;
         }
-        rows.emplace_back((size_t)n);
-        for (int k = 0; k < n; k++)
-            if (!read_real(f[k], rows.back()[k])) {
-                field_error(r, "APERTURE MAP", k + 1, "LINE - " + fixed(rec, 70) + "...");
+        const size_t nl = lines.size();
+        std::vector<std::vector<double>> parsed(nl);
+        std::vector<int> nf(nl, 0), bad(nl, 0);
+        const unsigned T = nl > 256 ? io_threads() : 1;
+        parallel_ranges((long long)nl, T, [&](long long b, long long e, unsigned) {
+            for (long long k = b; k < e; k++)
+                nf[(size_t)k] = parse_map_line(text.data() + lines[(size_t)k].first, text.data() + lines[(size_t)k].second,
+                                               r.maxdim + 1, parsed[(size_t)k], &bad[(size_t)k]);
+        });
+        // replay the records in order so the first failure is the one the reference would report
+        for (size_t k = 0; k < nl; k++) {
+            if (nf[k] == 0) continue;   // blank / comment-only record
+            if (nf[k] > r.maxdim) return horizontal();
+            if ((int)rows.size() + 1 > r.maxdim) return vertical();
+            if (bad[k]) {
+                field_error(r, "APERTURE MAP", bad[k],
+                            "LINE - " + fixed(upper(rtrim(text.substr(lines[k].first, lines[k].second - lines[k].first))), 70) + "...");
                 return false;
             }
-        nx = n;   // the width of the LAST record wins, like the reference
+            rows.emplace_back(std::move(parsed[k]));
+            nx = nf[k];   // the width of the LAST record wins, like the reference
+        }
     }
     r.nz = (int)rows.size();
     r.nx = nx;
@@ -611,24 +741,29 @@ void map_stats(const std::vector<double> &m, int nx, int nz, double &rms, double
     const double var = (sms - sm) * (1.0 / (cells - 1));
     dev = std::sqrt(var);
     const int kmax = (int)((double)std::min(nx, nz) / 2.0) + 1;
+    const unsigned T = (size_t)nx * nz > (1u << 18) ? io_threads() : 1;
     for (int dir = 0; dir < 2; dir++) {
         double t1 = 0, t2 = 0, t3 = 0, c = 0;
         for (int k = 1; k <= kmax; k++) {
-            double cnt = 0, ss = 0;
-            if (dir == 0) {
-                for (int z = 0; z < nz; z++)
-                    for (int x = 0; x + k < nx; x++) {
-                        const double d = m[(size_t)z * nx + x] - m[(size_t)z * nx + x + k];
-                        ss += d * d;
-                        cnt += 1;
+            // sum of squared differences at lag k; rows are split over threads, partial sums added in
+            // a fixed order (the O(N*K) variogram is the next host hotspot once the solve is fast)
+            const int zmax = dir == 0 ? nz : nz - k, xmax = dir == 0 ? nx - k : nx;
+            double cnt = zmax > 0 && xmax > 0 ? (double)zmax * (double)xmax : 0.0, ss = 0;
+            if (cnt > 0) {
+                std::vector<double> part(T, 0.0);
+                const size_t off = dir == 0 ? (size_t)k : (size_t)k * nx;
+                parallel_ranges(zmax, T, [&](long long zb, long long ze, unsigned slot) {
+                    double acc = 0;
+                    for (long long z = zb; z < ze; z++) {
+                        const double *row = &m[(size_t)z * nx];
+                        for (int x = 0; x < xmax; x++) {
+                            const double d = row[x] - row[x + off];
+                            acc += d * d;
+                        }
                     }
-            } else {
-                for (int z = 0; z + k < nz; z++)
-                    for (int x = 0; x < nx; x++) {
-                        const double d = m[(size_t)z * nx + x] - m[(size_t)(z + k) * nx + x];
-                        ss += d * d;
-                        cnt += 1;
-                    }
+                    part[slot] = acc;
+                });
+                for (double pp : part) ss += pp;
             }
             if (cnt == 0) continue;
             const double v3 = ss / cnt;
@@ -662,34 +797,27 @@ void write_percentile_table(Run &r, const std::vector<double> &pct, const std::v
 
 void write_map_csv(FILE *f, const double *v, int nx, int nz, double scale)
 {
-    std::string line;
-    line.reserve((size_t)nx * 16 + 2);
-    for (int z = 0; z < nz; z++) {
-        line.clear();
+    write_rows_parallel(f, nz, [=](long long z, std::string &line) {
         for (int x = 0; x < nx; x++) {
             if (x) line += ',';
             line += G(15, 8, v[(size_t)z * nx + x] * scale);
         }
         line += '\n';
-        fwrite(line.data(), 1, line.size(), f);
-    }
+    });
 }
 
 void write_vtk_scalars(Run &r, const char *name, const std::string &unit, const char *dtype, const double *v, double scale)
 {
     FILE *f = r.fvtk;
     fprintf(f, " \nSCALARS %s[%s] %s\nLOOKUP_TABLE default\n", name, unit.c_str(), dtype);
-    const size_t n = (size_t)r.nx * r.nz;
-    std::string buf;
-    buf.reserve(n * 16);
     // "(*(1(E14.6,:,' '), /, :))" : one value per record, followed by the separator blank
-    for (int z = 0; z < r.nz; z++) {
-        for (int x = 0; x < r.nx; x++) {
-            buf += E(14, 6, v[(size_t)z * r.nx + x] * scale);
-            buf += x + 1 < r.nx ? " \n" : "\n";
+    const int nx = r.nx;
+    write_rows_parallel(f, r.nz, [=](long long z, std::string &buf) {
+        for (int x = 0; x < nx; x++) {
+            buf += E(14, 6, v[(size_t)z * nx + x] * scale);
+            buf += x + 1 < nx ? " \n" : "\n";
         }
-    }
-    fwrite(buf.data(), 1, buf.size(), f);
+    });
     r.message(std::string("         ") + name + " DATA OUTPUT TO VTK FILE");
 }
 
@@ -995,24 +1123,22 @@ int run(Run &r, int device)
                 nx + 1, nz + 1, (long long)(nx + 1) * (nz + 1) * 2);
         const double pm = vox * r.dim_conv;
         const double dx = diam / nx * r.dim_conv, dz = leng / nz * r.dim_conv;
-        std::string buf;
-        auto point = [&](double X, double Y, double Z) { buf += E(14, 6, X) + " " + E(14, 6, Y) + " " + E(14, 6, Z) + "\n"; };
+        // X and Z are running sums in the reference (X = X + DX); reproduce the same partial sums
+        std::vector<double> xs((size_t)nx + 1), zs((size_t)nz + 1);
+        xs[0] = 0.0;
+        for (int ix = 0; ix < nx; ix++) xs[ix + 1] = xs[ix] + dx;
+        zs[0] = 0.0;
+        for (int iz = 0; iz < nz; iz++) zs[iz + 1] = zs[iz] + dz;
         for (int sgn = -1; sgn <= 1; sgn += 2) {
-            double Z = 0.0;
-            for (int iz = 0; iz <= nz; iz++) {
+            write_rows_parallel(f, (long long)nz + 1, [&, sgn](long long iz, std::string &buf) {
                 // rows 0..nz-1 use the bottom corners of row iz, the last record the top corners of row nz-1
-                const int cz = iz < nz ? iz - 1 : nz - 1;
-                double X = 0.0;
-                point(X, sgn * (corner(clamped, nx, nz, cz, -1) * pm) / 2.0, Z);
-                for (int ix = 0; ix < nx; ix++) {
-                    X = X + dx;
-                    point(X, sgn * (corner(clamped, nx, nz, cz, ix) * pm) / 2.0, Z);
-                }
-                if (iz < nz) Z = Z + dz;
-                if (buf.size() > (1u << 20)) { fwrite(buf.data(), 1, buf.size(), f); buf.clear(); }
-            }
+                const int cz = iz < nz ? (int)iz - 1 : nz - 1;
+                const double Z = zs[(size_t)iz];
+                for (int ix = -1; ix < nx; ix++)
+                    buf += E(14, 6, xs[(size_t)(ix + 1)]) + " " + E(14, 6, sgn * (corner(clamped, nx, nz, cz, ix) * pm) / 2.0) +
+                           " " + E(14, 6, Z) + "\n";
+            });
         }
-        fwrite(buf.data(), 1, buf.size(), f);
         r.message("         VTK POINTS OUTPUT TO FILE");
         r.blank();
         r.message("     OUTPUTTING DATA TO THE VTK FILE...");
@@ -1022,12 +1148,16 @@ int run(Run &r, int device)
         write_vtk_scalars(r, "REYNOLDS_NUMBER", "-", "float", ren.data(), 1.0);
         write_vtk_scalars(r, "NORMALIZED_RESIDUAL", "-", "float", res.data(), 1.0);
         fprintf(f, " \nVECTORS FLOW[%s] float\n", rtrim(r.unit_out[5]).c_str());
-        buf.clear();
-        for (size_t i = 0; i < n; i++) {
-            buf += E(14, 6, qx[i] * r.rate_conv) + " " + E(14, 6, 0.0) + " " + E(14, 6, qz[i] * r.rate_conv) + "\n";
-            if (buf.size() > (1u << 20)) { fwrite(buf.data(), 1, buf.size(), f); buf.clear(); }
+        {
+            const double rc = r.rate_conv;
+            const double *px = qx.data(), *pz = qz.data();
+            write_rows_parallel(f, nz, [=](long long z, std::string &b2) {
+                for (int x = 0; x < nx; x++) {
+                    const size_t i = (size_t)z * nx + x;
+                    b2 += E(14, 6, px[i] * rc) + " " + E(14, 6, 0.0) + " " + E(14, 6, pz[i] * rc) + "\n";
+                }
+            });
         }
-        fwrite(buf.data(), 1, buf.size(), f);
         r.message("         VECTOR FLOW DATA OUTPUT TO VTK FILE");
     }
     r.blank();

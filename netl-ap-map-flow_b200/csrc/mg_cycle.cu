@@ -380,44 +380,57 @@ k_smooth5_up(Fine5 v, const double *__restrict__ b, const double *__restrict__ x
         __syncthreads();
         add_prolongation<H, W>(sx, w, e, nzc, nxc, z0 - 2, x0 - 2, nz, nx);
         __syncthreads();
-        // black pass over tile + first halo ring
-        constexpr int W1 = kSmTX + 2, H1 = kSmTZ + 2;
-        for (int k = tid; k < H1 * W1; k += blockDim.x) {
-            const int lz = k / W1 - 1, lx = k % W1 - 1;
-            const int z = z0 + lz, xx = x0 + lx;
-            if (z >= 0 && z < nz && xx >= 0 && xx < nx && ((z + xx) & 1) == 1) {
+        // black pass over tile + first halo ring: lanes walk the black cells only (33 per framed row)
+        constexpr int H1 = kSmTZ + 2, NB = kSmTX / 2 + 1;
+        for (int k = tid; k < H1 * NB; k += blockDim.x) {
+            const int lz = k / NB - 1, cidx = k % NB;
+            const int z = z0 + lz;
+            const int lx = 2 * cidx - ((z + 1) & 1);      // x0 is even: (z + x) odd  <=>  lx has the parity of z + 1
+            const int xx = x0 + lx;
+            if (z >= 0 && z < nz && xx >= 0 && xx < nx) {
                 const size_t i = (size_t)z * nx + xx;
-                const double *p = &sx[(lz + 2) * W + lx + 2];
+                double *p = &sx[(lz + 2) * W + lx + 2];
                 const double tl = A.left(z, xx), tr = A.right(z, xx), td = A.down(z, xx), tu = A.up(z, xx);
                 double s = b[i];
                 if (xx > 0) s += tl * p[-1];
                 if (xx + 1 < nx) s += tr * p[1];
                 if (z > 0) s += td * p[-W];
                 if (z + 1 < nz) s += tu * p[W];
-                sx[(lz + 2) * W + lx + 2] = s / ((tl + tr) + (td + tu));
+                p[0] = s / ((tl + tr) + (td + tu));
             }
         }
         __syncthreads();
-        // red pass, tile interior, and the dot product over every interior cell
-        for (int k = tid; k < kSmTZ * kSmTX; k += blockDim.x) {
-            const int lz = k / kSmTX, lx = k % kSmTX;
-            const int z = z0 + lz, xx = x0 + lx;
-            if (z < nz && xx < nx) {
-                const size_t i = (size_t)z * nx + xx;
-                const double *p = &sx[(lz + 2) * W + lx + 2];
-                const double bi = b[i];
-                double xi = p[0];
-                if (((z + xx) & 1) == 0) {
-                    const double tl = A.left(z, xx), tr = A.right(z, xx), td = A.down(z, xx), tu = A.up(z, xx);
-                    double s = bi;
-                    if (xx > 0) s += tl * p[-1];
-                    if (xx + 1 < nx) s += tr * p[1];
-                    if (z > 0) s += td * p[-W];
-                    if (z + 1 < nz) s += tu * p[W];
-                    xi = s / ((tl + tr) + (td + tu));
-                }
-                xout[i] = xi;       // out of place: neighbouring tiles still read xin for their halos
-                acc[0] += bi * xi;
+        // red pass: each lane owns a horizontal pair (one red cell to update, one black cell to copy),
+        // accumulates b.x over both and writes them out of place
+        for (int k = tid; k < kSmTZ * kSmTX / 2; k += blockDim.x) {
+            const int lz = k / (kSmTX / 2), lx = 2 * (k % (kSmTX / 2));
+            const int z = z0 + lz, xe = x0 + lx;
+            if (z >= nz || xe >= nx) continue;
+            const size_t i = (size_t)z * nx + xe;
+            const double *p = &sx[(lz + 2) * W + lx + 2];
+            const bool hasO = xe + 1 < nx;
+            const int r = (z + xe) & 1;                   // 0: the even cell is red, 1: the odd cell is red
+            const int xr = xe + r;
+            double v0 = p[0], v1 = p[1];
+            if (xr < nx) {
+                const size_t ir = i + r;
+                const double *q = p + r;
+                const double tl = A.left(z, xr), tr = A.right(z, xr), td = A.down(z, xr), tu = A.up(z, xr);
+                double s = b[ir];
+                if (xr > 0) s += tl * q[-1];
+                if (xr + 1 < nx) s += tr * q[1];
+                if (z > 0) s += td * q[-W];
+                if (z + 1 < nz) s += tu * q[W];
+                const double xn = s / ((tl + tr) + (td + tu));
+                if (r) v1 = xn; else v0 = xn;
+            }
+            acc[0] += b[i] * v0;
+            if (hasO) acc[0] += b[i + 1] * v1;
+            if (hasO && !(nx & 1)) {
+                *reinterpret_cast<double2 *>(xout + i) = make_double2(v0, v1);   // i even when nx even: aligned
+            } else {
+                xout[i] = v0;
+                if (hasO) xout[i + 1] = v1;
             }
         }
         __syncthreads();

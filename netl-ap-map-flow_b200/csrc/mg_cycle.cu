@@ -190,86 +190,142 @@ __device__ __forceinline__ double prolong_value(const Weights &w, const double *
 
 constexpr int kSmTZ = 16, kSmTX = 64;   // smoother tile: 1024 points, 256 threads
 
-// sx (H x W doubles, H and W even) covers the fine cells from (zr, xr), both even (possibly -2):
-// add P e to it, one thread per coarse 2x2 block so the 8 weights and 4 coarse values are loaded once
+// sx (H x W doubles, H and W even) covers the fine cells from (zr, xr), both even (possibly -2).
+// sx := x + P e over the same framed region, in one pass: the thread that owns a coarse 2x2 block loads
+// its four x values together with the weights and coarse values (all loads independent, in flight
+// together) and writes the block once -- no read-modify-write of shared memory, no extra barrier.
 template <int H, int W>
-__device__ __forceinline__ void add_prolongation(double *sx, const Weights &w, const double *__restrict__ e, int nzc,
-                                                 int nxc, int zr, int xr, int nz, int nx)
+__device__ __forceinline__ void load_prolonged(double *sx, const double *__restrict__ xin, const Weights &w,
+                                               const double *__restrict__ e, int nzc, int nxc, int zr, int xr, int nz,
+                                               int nx)
 {
     constexpr int BH = H / 2, BW = W / 2;
     const int bz0 = zr >> 1, bx0 = xr >> 1;   // arithmetic shift: -2 >> 1 == -1
     for (int k = threadIdx.x; k < BH * BW; k += blockDim.x) {
         const int bzl = k / BW, bxl = k % BW;
         const int bz = bz0 + bzl, bx = bx0 + bxl;
-        if (bz < 0 || bx < 0 || bz >= nzc || bx >= nxc) continue;
-        const size_t b = (size_t)bz * nxc + bx;
-        const bool Xp = bx + 1 < nxc, Zp = bz + 1 < nzc;
-        const bool xp = 2 * bx + 1 < nx, zp = 2 * bz + 1 < nz;
-        const double e00 = e[b];
-        const double e01 = Xp ? e[b + 1] : 0.0;
-        const double e10 = Zp ? e[b + nxc] : 0.0;
-        const double e11 = (Zp && Xp) ? e[b + nxc + 1] : 0.0;
-        double *p = &sx[(2 * bzl) * W + 2 * bxl];
-        p[0] += e00;
-        if (xp) p[1] += w.hw[b] * e00 + w.he[b] * e01;
-        if (zp) p[W] += w.vs[b] * e00 + w.vn[b] * e10;
-        if (zp && xp) p[W + 1] += (w.csw[b] * e00 + w.cse[b] * e01) + (w.cnw[b] * e10 + w.cne[b] * e11);
+        double v00 = 0.0, v01 = 0.0, v10 = 0.0, v11 = 0.0;
+        if (bz >= 0 && bx >= 0 && bz < nzc && bx < nxc) {
+            const size_t b = (size_t)bz * nxc + bx;
+            const size_t i = (size_t)(2 * bz) * nx + 2 * bx;
+            const bool Xp = bx + 1 < nxc, Zp = bz + 1 < nzc;
+            const bool xp = 2 * bx + 1 < nx, zp = 2 * bz + 1 < nz;
+            const double e00 = e[b];
+            const double e01 = Xp ? e[b + 1] : 0.0;
+            const double e10 = Zp ? e[b + nxc] : 0.0;
+            const double e11 = (Zp && Xp) ? e[b + nxc + 1] : 0.0;
+            v00 = xin[i] + e00;
+            if (xp) v01 = xin[i + 1] + (w.hw[b] * e00 + w.he[b] * e01);
+            if (zp) v10 = xin[i + nx] + (w.vs[b] * e00 + w.vn[b] * e10);
+            if (zp && xp) v11 = xin[i + nx + 1] + ((w.csw[b] * e00 + w.cse[b] * e01) + (w.cnw[b] * e10 + w.cne[b] * e11));
+        }
+        double *p = &sx[(2 * bzl) * W + 2 * bxl];           // even offset: 16-byte aligned
+        *reinterpret_cast<double2 *>(p) = make_double2(v00, v01);
+        *reinterpret_cast<double2 *>(p + W) = make_double2(v10, v11);
     }
 }
 
+// Everything one cell of a 9-point level needs for a Gauss-Seidel update, held in registers for the
+// whole launch: the 8 couplings (W, E, S, N, SW, SE, NW, NE), the right-hand side and 1/diag.  Cells
+// outside the grid get all zeros, so their "update" is 0 and the sweeps need no bounds checks.
+struct Cell9 {
+    double gw, ge, gs, gn, gsw, gse, gnw, gne, b, inv;
+};
+__device__ __forceinline__ Cell9 load_cell9(const Coarse9 &v, const double *__restrict__ b, int z, int x)
+{
+    Cell9 c{0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+    const int nx = v.nx;
+    if (z < v.nz && x < nx) {
+        const size_t i = (size_t)z * nx + x;
+        const bool xm = x > 0, xp = x + 1 < nx, zm = z > 0;
+        c.ge = v.E[i];                       // E, N, NE, NW are stored 0 where the neighbour is absent
+        c.gn = v.N[i];
+        c.gne = v.NE[i];
+        c.gnw = v.NW[i];
+        if (xm) c.gw = v.E[i - 1];
+        if (zm) {
+            c.gs = v.N[i - nx];
+            if (xm) c.gsw = v.NE[i - nx - 1];
+            if (xp) c.gse = v.NW[i - nx + 1];
+        }
+        c.b = b[i];
+        c.inv = 1.0 / v.C[i];
+    }
+    return c;
+}
+template <int W>
+__device__ __forceinline__ void relax9(const Cell9 &c, double *p)
+{
+    double s = c.b;
+    s += c.gw * p[-1] + c.ge * p[1];
+    s += c.gs * p[-W] + c.gn * p[W];
+    s += c.gsw * p[-W - 1] + c.gse * p[-W + 1];
+    s += c.gnw * p[W - 1] + c.gne * p[W + 1];
+    p[0] = s * c.inv;
+}
+
 // All four colours and all `nu` sweeps of one 9-point level in ONE launch.  Each block owns a
-// 16x64 tile, keeps x (+1 halo) in shared memory and runs four-colour Gauss-Seidel on it; halo
+// 16x64 tile, keeps x (+ frame) in shared memory and runs four-colour Gauss-Seidel on it; halo
 // values stay frozen during the launch (hybrid GS: Jacobi between tiles, GS inside -- a regular
-// splitting, and the backward variant is its transpose, so the cycle stays symmetric).
+// splitting, and the backward variant is its transpose, so the cycle stays symmetric).  A thread
+// owns one 2x2 block (one cell of each colour) and loads its operator rows ONCE, all loads in
+// flight together; the sweeps then touch only registers and shared memory.
 // ZERO_INIT: x starts from 0 (down leg; nothing is read).  PROLONG: x starts from x + P e (up leg).
-template <bool ZERO_INIT, bool PROLONG>
-__global__ void __launch_bounds__(256, 4)
+template <bool ZERO_INIT, bool PROLONG, bool FORWARD>
+__global__ void __launch_bounds__(256, 2)
 k_smooth9(Coarse9 v, const double *__restrict__ b, const double *__restrict__ xin, double *__restrict__ xout, int nu,
-          int forward, Weights w, const double *__restrict__ e, int nzc, int nxc, const PcgState *st)
+          Weights w, const double *__restrict__ e, int nzc, int nxc, const PcgState *st)
 {
     if (stopped(st)) return;
-    const C9 A{v};
     const int nz = v.nz, nx = v.nx;
     constexpr int W = kSmTX + 4, H = kSmTZ + 4;   // 2-cell frame keeps the region aligned to coarse blocks
-    __shared__ double sx[H * W];
+    alignas(16) __shared__ double sx[H * W];
     const int tiles_x = (nx + kSmTX - 1) / kSmTX, tiles_z = (nz + kSmTZ - 1) / kSmTZ;
     const int tid = threadIdx.x;
+    const int a = tid >> 5, c = tid & 31;
     for (long long t = blockIdx.x; t < (long long)tiles_x * tiles_z; t += gridDim.x) {
         const int z0 = (int)(t / tiles_x) * kSmTZ, x0 = (int)(t % tiles_x) * kSmTX;
-        for (int k = tid; k < H * W; k += blockDim.x) {
-            const int z = z0 + k / W - 2, xx = x0 + k % W - 2;
-            double val = 0.0;
-            if (!ZERO_INIT && z >= 0 && z < nz && xx >= 0 && xx < nx)
-                val = xin[(size_t)z * nx + xx];     // never the array this launch writes: other tiles read it
-            sx[k] = val;
-        }
+        const int z = z0 + 2 * a, xx = x0 + 2 * c;
+        const Cell9 c00 = load_cell9(v, b, z, xx), c01 = load_cell9(v, b, z, xx + 1);
+        const Cell9 c10 = load_cell9(v, b, z + 1, xx), c11 = load_cell9(v, b, z + 1, xx + 1);
         if (PROLONG) {
-            __syncthreads();
-            add_prolongation<H, W>(sx, w, e, nzc, nxc, z0 - 2, x0 - 2, nz, nx);
+            load_prolonged<H, W>(sx, xin, w, e, nzc, nxc, z0 - 2, x0 - 2, nz, nx);
+        } else {
+            for (int k = tid; k < H * W; k += blockDim.x) {
+                const int zf = z0 + k / W - 2, xf = x0 + k % W - 2;
+                double val = 0.0;
+                if (!ZERO_INIT && zf >= 0 && zf < nz && xf >= 0 && xf < nx)
+                    val = xin[(size_t)zf * nx + xf];     // never the array this launch writes: other tiles read it
+                sx[k] = val;
+            }
         }
         __syncthreads();
-        const int a = tid >> 5, c = tid & 31;
-        for (int sweep = 0; sweep < nu; sweep++)
-            for (int step = 0; step < 4; step++) {
-                const int col = forward ? step : 3 - step;
-                const int lz = 2 * a + (col >> 1), lx = 2 * c + (col & 1);
-                const int z = z0 + lz, xx = x0 + lx;
-                if (z < nz && xx < nx) {
-                    const size_t i = (size_t)z * nx + xx;
-                    double *p = &sx[(lz + 2) * W + lx + 2];
-                    double s = b[i];
-                    s += A.g(z, xx, 0, -1) * p[-1] + A.g(z, xx, 0, 1) * p[1];
-                    s += A.g(z, xx, -1, 0) * p[-W] + A.g(z, xx, 1, 0) * p[W];
-                    s += A.g(z, xx, -1, -1) * p[-W - 1] + A.g(z, xx, -1, 1) * p[-W + 1];
-                    s += A.g(z, xx, 1, -1) * p[W - 1] + A.g(z, xx, 1, 1) * p[W + 1];
-                    p[0] = s / A.diag(z, xx);
-                }
+        double *p = &sx[(2 * a + 2) * W + 2 * c + 2];
+        for (int sweep = 0; sweep < nu; sweep++) {
+            if (FORWARD) {
+                relax9<W>(c00, p);
+                __syncthreads();
+                relax9<W>(c01, p + 1);
+                __syncthreads();
+                relax9<W>(c10, p + W);
+                __syncthreads();
+                relax9<W>(c11, p + W + 1);
+                __syncthreads();
+            } else {
+                relax9<W>(c11, p + W + 1);
+                __syncthreads();
+                relax9<W>(c10, p + W);
+                __syncthreads();
+                relax9<W>(c01, p + 1);
+                __syncthreads();
+                relax9<W>(c00, p);
                 __syncthreads();
             }
+        }
         for (int k = tid; k < kSmTZ * kSmTX; k += blockDim.x) {
             const int lz = k / kSmTX, lx = k % kSmTX;
-            const int z = z0 + lz, xx = x0 + lx;
-            if (z < nz && xx < nx) xout[(size_t)z * nx + xx] = sx[(lz + 2) * W + lx + 2];
+            const int zf = z0 + lz, xf = x0 + lx;
+            if (zf < nz && xf < nx) xout[(size_t)zf * nx + xf] = sx[(lz + 2) * W + lx + 2];
         }
         __syncthreads();
     }
@@ -293,47 +349,54 @@ k_smooth5_down(Fine5 v, const double *__restrict__ b, double *__restrict__ x, Pc
     double acc[2] = {0.0, 0.0};
     for (long long t = blockIdx.x; t < (long long)tiles_x * tiles_z; t += gridDim.x) {
         const int z0 = (int)(t / tiles_x) * kSmTZ, x0 = (int)(t % tiles_x) * kSmTX;
-        // red pass over tile + halo (colour 0 = (z+x) even); black cells start at 0
-        for (int k = tid; k < H * W; k += blockDim.x) {
-            const int lz = k / W - 1, lx = k % W - 1;
-            const int z = z0 + lz, xx = x0 + lx;
-            double val = 0.0;
-            if (z >= 0 && z < nz && xx >= 0 && xx < nx) {
-                const bool interior = lz >= 0 && lz < kSmTZ && lx >= 0 && lx < kSmTX;
-                const bool red = ((z + xx) & 1) == 0;
-                if (red || interior) {
-                    const double bi = b[(size_t)z * nx + xx];
-                    const double inv = 1.0 / A.diag(z, xx);
-                    if (red) val = bi * inv;
-                    if (interior) { acc[0] += bi * bi; acc[1] += bi * bi * inv; }
-                }
-            }
-            sx[k] = val;
-        }
-        __syncthreads();
-        // black pass, tile interior only
-        for (int k = tid; k < kSmTZ * kSmTX / 2; k += blockDim.x) {
-            const int lz = k / (kSmTX / 2);
+        // red pass over tile + halo ring (colour 0 = (z+x) even): lanes walk the red cells only.  From a
+        // zero guess red = b/diag needs no neighbour, so the ring is recomputed instead of exchanged.
+        constexpr int NR = kSmTX / 2 + 1;
+        for (int k = tid; k < H * NR; k += blockDim.x) {
+            const int lz = k / NR - 1, cidx = k % NR;
             const int z = z0 + lz;
-            const int lx = 2 * (k % (kSmTX / 2)) + ((z + 1) & 1);   // (z + x) odd, x0 is even
+            const int lx = 2 * cidx - (z & 1);             // x0 is even: (z + x) even  <=>  lx has the parity of z
             const int xx = x0 + lx;
-            if (z < nz && xx < nx) {
-                const size_t i = (size_t)z * nx + xx;
-                const double *p = &sx[(lz + 1) * W + lx + 1];
-                const double tl = A.left(z, xx), tr = A.right(z, xx), td = A.down(z, xx), tu = A.up(z, xx);
-                double s = b[i];
-                if (xx > 0) s += tl * p[-1];
-                if (xx + 1 < nx) s += tr * p[1];
-                if (z > 0) s += td * p[-W];
-                if (z + 1 < nz) s += tu * p[W];
-                sx[(lz + 1) * W + lx + 1] = s / ((tl + tr) + (td + tu));
+            if (z >= 0 && z < nz && xx >= 0 && xx < nx) {
+                const double bi = b[(size_t)z * nx + xx];
+                const double inv = 1.0 / A.diag(z, xx);
+                sx[(lz + 1) * W + lx + 1] = bi * inv;
+                if (lz >= 0 && lz < kSmTZ && lx >= 0 && lx < kSmTX) { acc[0] += bi * bi; acc[1] += bi * bi * inv; }
             }
         }
         __syncthreads();
-        for (int k = tid; k < kSmTZ * kSmTX; k += blockDim.x) {
-            const int lz = k / kSmTX, lx = k % kSmTX;
-            const int z = z0 + lz, xx = x0 + lx;
-            if (z < nz && xx < nx) x[(size_t)z * nx + xx] = sx[(lz + 1) * W + lx + 1];
+        // black pass, tile interior: each lane owns a horizontal pair (one black cell to update, its red
+        // neighbour to copy) and writes both out of place
+        for (int k = tid; k < kSmTZ * kSmTX / 2; k += blockDim.x) {
+            const int lz = k / (kSmTX / 2), lx = 2 * (k % (kSmTX / 2));
+            const int z = z0 + lz, xe = x0 + lx;
+            if (z >= nz || xe >= nx) continue;
+            const size_t i = (size_t)z * nx + xe;
+            const double *p = &sx[(lz + 1) * W + lx + 1];
+            const bool hasO = xe + 1 < nx;
+            const int r = ((z + xe) & 1) ^ 1;             // 0: the even cell is black, 1: the odd cell is black
+            const int xb = xe + r;
+            double v0 = r ? p[0] : 0.0, v1 = r ? 0.0 : (hasO ? p[1] : 0.0);
+            if (xb < nx) {
+                const double *q = p + r;
+                const double tl = A.left(z, xb), tr = A.right(z, xb), td = A.down(z, xb), tu = A.up(z, xb);
+                const double bi = b[i + r];
+                double s = bi;
+                if (xb > 0) s += tl * q[-1];
+                if (xb + 1 < nx) s += tr * q[1];
+                if (z > 0) s += td * q[-W];
+                if (z + 1 < nz) s += tu * q[W];
+                const double inv = 1.0 / ((tl + tr) + (td + tu));
+                acc[0] += bi * bi;
+                acc[1] += bi * bi * inv;
+                if (r) v1 = s * inv; else v0 = s * inv;
+            }
+            if (hasO && !(nx & 1)) {
+                *reinterpret_cast<double2 *>(x + i) = make_double2(v0, v1);   // i even when nx even: aligned
+            } else {
+                x[i] = v0;
+                if (hasO) x[i + 1] = v1;
+            }
         }
         __syncthreads();
     }
@@ -367,18 +430,13 @@ k_smooth5_up(Fine5 v, const double *__restrict__ b, const double *__restrict__ x
     const F5 A{v};
     const int nz = v.nz, nx = v.nx;
     constexpr int W = kSmTX + 4, H = kSmTZ + 4;
-    __shared__ double sx[H * W];
+    alignas(16) __shared__ double sx[H * W];
     const int tiles_x = (nx + kSmTX - 1) / kSmTX, tiles_z = (nz + kSmTZ - 1) / kSmTZ;
     const int tid = threadIdx.x;
     double acc[2] = {0.0, 0.0};
     for (long long t = blockIdx.x; t < (long long)tiles_x * tiles_z; t += gridDim.x) {
         const int z0 = (int)(t / tiles_x) * kSmTZ, x0 = (int)(t % tiles_x) * kSmTX;
-        for (int k = tid; k < H * W; k += blockDim.x) {
-            const int z = z0 + k / W - 2, xx = x0 + k % W - 2;
-            sx[k] = (z >= 0 && z < nz && xx >= 0 && xx < nx) ? xin[(size_t)z * nx + xx] : 0.0;
-        }
-        __syncthreads();
-        add_prolongation<H, W>(sx, w, e, nzc, nxc, z0 - 2, x0 - 2, nz, nx);
+        load_prolonged<H, W>(sx, xin, w, e, nzc, nxc, z0 - 2, x0 - 2, nz, nx);
         __syncthreads();
         // black pass over tile + first halo ring: lanes walk the black cells only (33 per framed row)
         constexpr int H1 = kSmTZ + 2, NB = kSmTX / 2 + 1;
@@ -619,8 +677,8 @@ double bench_launch_cycle(Solver &s, const std::string &name)
     }
     if (name == "smooth9_l1" && s.levels.size() > 2) {
         Level &f = s.levels[1];
-        LAUNCH((k_smooth9<true, false>), tile_grid(f.nz, f.nx), 256, 0, s.stream, f.view9(), (const double *)f.b,
-               (const double *)nullptr, f.x, s.nu_coarse, 1, Weights{}, (const double *)nullptr, 0, 0,
+        LAUNCH((k_smooth9<true, false, true>), tile_grid(f.nz, f.nx), 256, 0, s.stream, f.view9(), (const double *)f.b,
+               (const double *)nullptr, f.x, s.nu_coarse, Weights{}, (const double *)nullptr, 0, 0,
                (const PcgState *)s.state);
         return 56.0 * (double)f.n;   // b, C, E, N, NE, NW in; x out (couplings re-read from L1/L2 per sweep)
     }
@@ -632,8 +690,8 @@ double bench_launch_cycle(Solver &s, const std::string &name)
     }
     if (name == "smooth9_l1_up" && s.levels.size() > 2) {
         Level &f = s.levels[1], &c = s.levels[2];
-        LAUNCH((k_smooth9<false, true>), tile_grid(f.nz, f.nx), 256, 0, s.stream, f.view9(), (const double *)f.b,
-               (const double *)f.x, f.r, s.nu_coarse, 0, f.w, (const double *)c.r, c.nz, c.nx, (const PcgState *)s.state);
+        LAUNCH((k_smooth9<false, true, false>), tile_grid(f.nz, f.nx), 256, 0, s.stream, f.view9(), (const double *)f.b,
+               (const double *)f.x, f.r, s.nu_coarse, f.w, (const double *)c.r, c.nz, c.nx, (const PcgState *)s.state);
         return 64.0 * (double)f.n + (8.0 + 64.0) * (double)c.n;
     }
     if (name == "residual9_l1" && s.levels.size() > 2) {
@@ -735,8 +793,8 @@ void mg_vcycle(Solver &s, const double *r, double *ztmp, double *zout, PcgState 
     const Weights now{};
     for (size_t l = 1; l + 1 < nlev; l++) {
         Level &f = s.levels[l], &c = s.levels[l + 1];
-        LAUNCH((k_smooth9<true, false>), tile_grid(f.nz, f.nx), 256, 0, s.stream, f.view9(), (const double *)f.b,
-               (const double *)nullptr, f.x, l == 1 ? s.nu_coarse : s.nu_deep, 1, now, (const double *)nullptr, 0, 0,
+        LAUNCH((k_smooth9<true, false, true>), tile_grid(f.nz, f.nx), 256, 0, s.stream, f.view9(), (const double *)f.b,
+               (const double *)nullptr, f.x, l == 1 ? s.nu_coarse : s.nu_deep, now, (const double *)nullptr, 0, 0,
                (const PcgState *)st);
         LAUNCH(k_residual9, grid_for(s, f.nz, f.nx, 8), kBlock, 0, s.stream, f.view9(), (const double *)f.b,
                (const double *)f.x, f.r, st);
@@ -750,8 +808,8 @@ void mg_vcycle(Solver &s, const double *r, double *ztmp, double *zout, PcgState 
     }
     for (size_t l = nlev - 2; l >= 1; l--) {
         Level &f = s.levels[l], &c = s.levels[l + 1];
-        LAUNCH((k_smooth9<false, true>), tile_grid(f.nz, f.nx), 256, 0, s.stream, f.view9(), (const double *)f.b,
-               (const double *)f.x, f.r, l == 1 ? s.nu_coarse : s.nu_deep, 0, f.w, (const double *)c.r, c.nz, c.nx,
+        LAUNCH((k_smooth9<false, true, false>), tile_grid(f.nz, f.nx), 256, 0, s.stream, f.view9(), (const double *)f.b,
+               (const double *)f.x, f.r, l == 1 ? s.nu_coarse : s.nu_deep, f.w, (const double *)c.r, c.nz, c.nx,
                (const PcgState *)st);
     }
     {

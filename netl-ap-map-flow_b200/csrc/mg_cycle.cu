@@ -189,6 +189,7 @@ __device__ __forceinline__ double prolong_value(const Weights &w, const double *
 }
 
 constexpr int kSmTZ = 16, kSmTX = 64;   // smoother tile: 1024 points, 256 threads
+constexpr int kSmThreads = 256;         // compile-time so the per-tile loops unroll and batch their loads
 
 // sx (H x W doubles, H and W even) covers the fine cells from (zr, xr), both even (possibly -2).
 // sx := x + P e over the same framed region, in one pass: the thread that owns a coarse 2x2 block loads
@@ -201,7 +202,8 @@ __device__ __forceinline__ void load_prolonged(double *sx, const double *__restr
 {
     constexpr int BH = H / 2, BW = W / 2;
     const int bz0 = zr >> 1, bx0 = xr >> 1;   // arithmetic shift: -2 >> 1 == -1
-    for (int k = threadIdx.x; k < BH * BW; k += blockDim.x) {
+    #pragma unroll
+    for (int k = threadIdx.x; k < BH * BW; k += kSmThreads) {
         const int bzl = k / BW, bxl = k % BW;
         const int bz = bz0 + bzl, bx = bx0 + bxl;
         double v00 = 0.0, v01 = 0.0, v10 = 0.0, v11 = 0.0;
@@ -291,7 +293,7 @@ k_smooth9(Coarse9 v, const double *__restrict__ b, const double *__restrict__ xi
         if (PROLONG) {
             load_prolonged<H, W>(sx, xin, w, e, nzc, nxc, z0 - 2, x0 - 2, nz, nx);
         } else {
-            for (int k = tid; k < H * W; k += blockDim.x) {
+            for (int k = tid; k < H * W; k += kSmThreads) {
                 const int zf = z0 + k / W - 2, xf = x0 + k % W - 2;
                 double val = 0.0;
                 if (!ZERO_INIT && zf >= 0 && zf < nz && xf >= 0 && xf < nx)
@@ -322,7 +324,7 @@ k_smooth9(Coarse9 v, const double *__restrict__ b, const double *__restrict__ xi
                 __syncthreads();
             }
         }
-        for (int k = tid; k < kSmTZ * kSmTX; k += blockDim.x) {
+        for (int k = tid; k < kSmTZ * kSmTX; k += kSmThreads) {
             const int lz = k / kSmTX, lx = k % kSmTX;
             const int zf = z0 + lz, xf = x0 + lx;
             if (zf < nz && xf < nx) xout[(size_t)zf * nx + xf] = sx[(lz + 2) * W + lx + 2];
@@ -352,7 +354,7 @@ k_smooth5_down(Fine5 v, const double *__restrict__ b, double *__restrict__ x, Pc
         // red pass over tile + halo ring (colour 0 = (z+x) even): lanes walk the red cells only.  From a
         // zero guess red = b/diag needs no neighbour, so the ring is recomputed instead of exchanged.
         constexpr int NR = kSmTX / 2 + 1;
-        for (int k = tid; k < H * NR; k += blockDim.x) {
+        for (int k = tid; k < H * NR; k += blockDim.x) {   // (fully unrolled it needs 60 registers: slower)
             const int lz = k / NR - 1, cidx = k % NR;
             const int z = z0 + lz;
             const int lx = 2 * cidx - (z & 1);             // x0 is even: (z + x) even  <=>  lx has the parity of z
@@ -422,7 +424,7 @@ k_smooth5_down(Fine5 v, const double *__restrict__ b, double *__restrict__ x, Pc
 // Fine level, up leg: x += P e, then one EXACT black/red sweep, and b.x (= r.z of PCG) in one launch.
 // The tile carries a 2-cell halo of x + P e so the black cells of the first halo ring can be updated
 // redundantly and the red cells of the tile see exactly what the two-pass version saw.
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(kSmThreads)
 k_smooth5_up(Fine5 v, const double *__restrict__ b, const double *__restrict__ xin, double *__restrict__ xout, Weights w,
              const double *__restrict__ e, int nzc, int nxc, PcgState *st, int init, double *partials, unsigned int *counter)
 {
@@ -440,7 +442,8 @@ k_smooth5_up(Fine5 v, const double *__restrict__ b, const double *__restrict__ x
         __syncthreads();
         // black pass over tile + first halo ring: lanes walk the black cells only (33 per framed row)
         constexpr int H1 = kSmTZ + 2, NB = kSmTX / 2 + 1;
-        for (int k = tid; k < H1 * NB; k += blockDim.x) {
+#pragma unroll
+        for (int k = tid; k < H1 * NB; k += kSmThreads) {
             const int lz = k / NB - 1, cidx = k % NB;
             const int z = z0 + lz;
             const int lx = 2 * cidx - ((z + 1) & 1);      // x0 is even: (z + x) odd  <=>  lx has the parity of z + 1
@@ -460,7 +463,8 @@ k_smooth5_up(Fine5 v, const double *__restrict__ b, const double *__restrict__ x
         __syncthreads();
         // red pass: each lane owns a horizontal pair (one red cell to update, one black cell to copy),
         // accumulates b.x over both and writes them out of place
-        for (int k = tid; k < kSmTZ * kSmTX / 2; k += blockDim.x) {
+#pragma unroll
+        for (int k = tid; k < kSmTZ * kSmTX / 2; k += kSmThreads) {
             const int lz = k / (kSmTX / 2), lx = 2 * (k % (kSmTX / 2));
             const int z = z0 + lz, xe = x0 + lx;
             if (z >= nz || xe >= nx) continue;
@@ -562,11 +566,16 @@ k_restrict_residual5(Fine5 v, Weights w, const double *__restrict__ b, const dou
         const int z = 2 * Z, xx = 2 * X;
         const size_t bk = (size_t)Z * nxc + X;
         const bool xm = X > 0, xp = xx + 1 < nx, zm = Z > 0, zp = z + 1 < nz;
+        // branch-free: absent diagonal centres are evaluated at a clamped (existing) cell with weight 0,
+        // so the ~50 loads of the five residuals are independent and can all be in flight together
+        const int zu = zp ? z + 1 : z, zd = zm ? z - 1 : z, xr = xp ? xx + 1 : xx, xl = xm ? xx - 1 : xx;
+        const double wne = (zp && xp) ? w.csw[bk] : 0.0, wnw = (zp && xm) ? w.cse[bk - 1] : 0.0;
+        const double wse = (zm && xp) ? w.cnw[bk - nxc] : 0.0, wsw = (zm && xm) ? w.cne[bk - nxc - 1] : 0.0;
         double s = residual5_at(A, b, x, z, xx, nz, nx);
-        if (zp && xp) s += w.csw[bk] * residual5_at(A, b, x, z + 1, xx + 1, nz, nx);
-        if (zp && xm) s += w.cse[bk - 1] * residual5_at(A, b, x, z + 1, xx - 1, nz, nx);
-        if (zm && xp) s += w.cnw[bk - nxc] * residual5_at(A, b, x, z - 1, xx + 1, nz, nx);
-        if (zm && xm) s += w.cne[bk - nxc - 1] * residual5_at(A, b, x, z - 1, xx - 1, nz, nx);
+        s += wne * residual5_at(A, b, x, zu, xr, nz, nx);
+        s += wnw * residual5_at(A, b, x, zu, xl, nz, nx);
+        s += wse * residual5_at(A, b, x, zd, xr, nz, nx);
+        s += wsw * residual5_at(A, b, x, zd, xl, nz, nx);
         bc[bk] = s;
     }
 }
@@ -666,18 +675,18 @@ double bench_launch_cycle(Solver &s, const std::string &name)
         return (int)(tiles < cap ? tiles : cap);
     };
     if (name == "smooth_down") {
-        LAUNCH(k_smooth5_down, tile_grid(s.nz, s.nx), 256, 0, s.stream, v5, (const double *)s.r, s.z, s.state, 0, part, cnt);
+        LAUNCH(k_smooth5_down, tile_grid(s.nz, s.nx), kSmThreads, 0, s.stream, v5, (const double *)s.r, s.z, s.state, 0, part, cnt);
         return 32.0 * n;   // b, tx, tz in; x out
     }
     if (name == "smooth_up" && s.levels.size() > 1 && s.levels[0].w.hw) {
         Level &c = s.levels[1];
-        LAUNCH(k_smooth5_up, tile_grid(s.nz, s.nx), 256, 0, s.stream, v5, (const double *)s.r, (const double *)s.z, s.q,
+        LAUNCH(k_smooth5_up, tile_grid(s.nz, s.nx), kSmThreads, 0, s.stream, v5, (const double *)s.r, (const double *)s.z, s.q,
                s.levels[0].w, (const double *)c.r, c.nz, c.nx, s.state, 0, part + 4 * kMaxPartials, cnt + 1);
         return 40.0 * n + (8.0 + 64.0) * (double)c.n;   // x, b, tx, tz in; x out; coarse e + 8 weights
     }
     if (name == "smooth9_l1" && s.levels.size() > 2) {
         Level &f = s.levels[1];
-        LAUNCH((k_smooth9<true, false, true>), tile_grid(f.nz, f.nx), 256, 0, s.stream, f.view9(), (const double *)f.b,
+        LAUNCH((k_smooth9<true, false, true>), tile_grid(f.nz, f.nx), kSmThreads, 0, s.stream, f.view9(), (const double *)f.b,
                (const double *)nullptr, f.x, s.nu_coarse, Weights{}, (const double *)nullptr, 0, 0,
                (const PcgState *)s.state);
         return 56.0 * (double)f.n;   // b, C, E, N, NE, NW in; x out (couplings re-read from L1/L2 per sweep)
@@ -690,7 +699,7 @@ double bench_launch_cycle(Solver &s, const std::string &name)
     }
     if (name == "smooth9_l1_up" && s.levels.size() > 2) {
         Level &f = s.levels[1], &c = s.levels[2];
-        LAUNCH((k_smooth9<false, true, false>), tile_grid(f.nz, f.nx), 256, 0, s.stream, f.view9(), (const double *)f.b,
+        LAUNCH((k_smooth9<false, true, false>), tile_grid(f.nz, f.nx), kSmThreads, 0, s.stream, f.view9(), (const double *)f.b,
                (const double *)f.x, f.r, s.nu_coarse, f.w, (const double *)c.r, c.nz, c.nx, (const PcgState *)s.state);
         return 64.0 * (double)f.n + (8.0 + 64.0) * (double)c.n;
     }
@@ -784,7 +793,7 @@ void mg_vcycle(Solver &s, const double *r, double *ztmp, double *zout, PcgState 
     // the halo), so each level ping-pongs: down leg x -> level.x, up leg result -> level.r (the
     // residual it held has been restricted by then).  Fine level: ztmp after the down leg, zout final;
     // zout doubles as the fine residual buffer in between.
-    LAUNCH(k_smooth5_down, tile_grid(s.nz, s.nx), 256, 0, s.stream, v5, r, ztmp, st, init, part, cnt);
+    LAUNCH(k_smooth5_down, tile_grid(s.nz, s.nx), kSmThreads, 0, s.stream, v5, r, ztmp, st, init, part, cnt);
     {
         Level &c = s.levels[1];
         LAUNCH(k_restrict_residual5, grid_for(s, c.nz, c.nx, 8), kBlock, 0, s.stream, v5, s.levels[0].w, r,
@@ -793,7 +802,7 @@ void mg_vcycle(Solver &s, const double *r, double *ztmp, double *zout, PcgState 
     const Weights now{};
     for (size_t l = 1; l + 1 < nlev; l++) {
         Level &f = s.levels[l], &c = s.levels[l + 1];
-        LAUNCH((k_smooth9<true, false, true>), tile_grid(f.nz, f.nx), 256, 0, s.stream, f.view9(), (const double *)f.b,
+        LAUNCH((k_smooth9<true, false, true>), tile_grid(f.nz, f.nx), kSmThreads, 0, s.stream, f.view9(), (const double *)f.b,
                (const double *)nullptr, f.x, l == 1 ? s.nu_coarse : s.nu_deep, now, (const double *)nullptr, 0, 0,
                (const PcgState *)st);
         LAUNCH(k_residual9, grid_for(s, f.nz, f.nx, 8), kBlock, 0, s.stream, f.view9(), (const double *)f.b,
@@ -808,13 +817,13 @@ void mg_vcycle(Solver &s, const double *r, double *ztmp, double *zout, PcgState 
     }
     for (size_t l = nlev - 2; l >= 1; l--) {
         Level &f = s.levels[l], &c = s.levels[l + 1];
-        LAUNCH((k_smooth9<false, true, false>), tile_grid(f.nz, f.nx), 256, 0, s.stream, f.view9(), (const double *)f.b,
+        LAUNCH((k_smooth9<false, true, false>), tile_grid(f.nz, f.nx), kSmThreads, 0, s.stream, f.view9(), (const double *)f.b,
                (const double *)f.x, f.r, l == 1 ? s.nu_coarse : s.nu_deep, f.w, (const double *)c.r, c.nz, c.nx,
                (const PcgState *)st);
     }
     {
         Level &c = s.levels[1];
-        LAUNCH(k_smooth5_up, tile_grid(s.nz, s.nx), 256, 0, s.stream, v5, r, (const double *)ztmp, zout, s.levels[0].w,
+        LAUNCH(k_smooth5_up, tile_grid(s.nz, s.nx), kSmThreads, 0, s.stream, v5, r, (const double *)ztmp, zout, s.levels[0].w,
                (const double *)c.r, c.nz, c.nx, st, init, part + 4 * kMaxPartials, cnt + 1);
     }
 }

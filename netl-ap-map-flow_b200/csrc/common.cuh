@@ -143,6 +143,7 @@ struct Solver {
     long long iter_graph_launches = 0;
     int nu_fine = 1, nu_coarse = 2, nu_deep = 2;   // sweeps: fine, level 1, levels >= 2
     bool have_solution = false;
+    bool down_configured = false;   // k_down5 opted in to >48 KB dynamic shared memory on this device
     apm_lcl_params last_params{};
     Fine5 view5() const { return Fine5{tx, tz, txl, tzb, nz, nx}; }
 };

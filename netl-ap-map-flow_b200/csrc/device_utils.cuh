@@ -11,6 +11,25 @@ constexpr int kBlock = kTileX * kTileZ;   // 256 threads, one cell each per tile
 
 __device__ __forceinline__ double ldcg(const double *p) { return __ldcg(p); }
 
+// 8-byte asynchronous global -> shared copy (LDGSTS: the data never passes through registers, so a
+// thread can have a whole tile's worth in flight); !pred zero-fills the destination instead.
+__device__ __forceinline__ void cp_async8(double *dst_smem, const double *src, bool pred)
+{
+#ifdef LCL_CPU_SIM
+    *dst_smem = pred ? *src : 0.0;
+#else
+    const unsigned d = (unsigned)__cvta_generic_to_shared(dst_smem);
+    const int nbytes = pred ? 8 : 0;
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(d), "l"(src), "r"(nbytes) : "memory");
+#endif
+}
+__device__ __forceinline__ void cp_async_wait_all()
+{
+#ifndef LCL_CPU_SIM
+    asm volatile("cp.async.wait_all;" ::: "memory");
+#endif
+}
+
 // ---------------------------------------------------------------------------------------------
 // 5-point fine operator accessors (all couplings are positive conductances)
 struct F5 {

@@ -333,6 +333,26 @@ k_smooth9(Coarse9 v, const double *__restrict__ b, const double *__restrict__ xi
     }
 }
 
+// What the down leg's reduction decides: the PCG residual norms and the stopping rule.
+__device__ __forceinline__ void down_norms_finalize(PcgState *st, int init, const double (&tot)[2])
+{
+    st->rr = tot[0];
+    st->rs = tot[1];
+    if (init) {
+        st->bb = tot[0];
+        st->bs = tot[1];
+    } else if (tot[0] <= st->tol2 * st->bb && tot[1] <= st->tol2 * st->bs) {
+        // Residual norms are met.  Keep iterating only while every update still shrinks the
+        // largest pointwise pressure change: that is how weakly connected cells (which global
+        // norms do not see) reach 1e-6.  If the change grows twice in a row (or after 12 such
+        // extra iterations) what is left are floating pockets, so stop.
+        st->res_ok += 1;
+        if ((st->dx <= st->dx_tol && st->dx_prev <= st->dx_tol) || (st->dx > st->dx_prev && st->dx_prev > st->dx_prev2) || st->res_ok > 12)
+            st->converged = 1;
+    }
+    if (!(tot[0] == tot[0]) || !(tot[1] == tot[1])) st->failed = 1;
+}
+
 // Fine level, down leg: one EXACT red/black sweep from a zero guess in one launch.
 // red = b/diag needs no neighbour, so the red values of the halo ring are recomputed from b and the
 // faces instead of being exchanged; black then sees exactly what the two-pass version saw.
@@ -402,23 +422,154 @@ k_smooth5_down(Fine5 v, const double *__restrict__ b, double *__restrict__ x, Pc
         }
         __syncthreads();
     }
-    grid_sum_finalize<2>(acc, partials, counter, [=](const double(&tot)[2]) {
-        st->rr = tot[0];
-        st->rs = tot[1];
-        if (init) {
-            st->bb = tot[0];
-            st->bs = tot[1];
-        } else if (tot[0] <= st->tol2 * st->bb && tot[1] <= st->tol2 * st->bs) {
-            // Residual norms are met.  Keep iterating only while every update still shrinks the
-            // largest pointwise pressure change: that is how weakly connected cells (which global
-            // norms do not see) reach 1e-6.  If the change grows twice in a row (or after 12 such
-            // extra iterations) what is left are floating pockets, so stop.
-            st->res_ok += 1;
-            if ((st->dx <= st->dx_tol && st->dx_prev <= st->dx_tol) || (st->dx > st->dx_prev && st->dx_prev > st->dx_prev2) || st->res_ok > 12)
-                st->converged = 1;
+    grid_sum_finalize<2>(acc, partials, counter, [=](const double(&tot)[2]) { down_norms_finalize(st, init, tot); });
+}
+
+// Fine level, whole down leg in ONE launch: exact red/black sweep from a zero guess, the residual it
+// leaves (non-zero at red cells only) and its restriction to the coarse right-hand side.
+// A block stages b and the faces of a 32x64 tile plus frame in shared memory with asynchronous copies
+// (everything in flight at once, zero-filled outside the grid, so the passes need no bounds logic and
+// touch no global memory), then recomputes the frame instead of exchanging it:
+//   red  (rows -3..TZ+1)  x = b/diag                    -> needs nothing else
+//   black(rows -2..TZ)    x = (b + sum t x_red)/diag    -> exactly what the two-pass version computes
+//   residual at red cells (rows -1..TZ-1), in place over b
+//   coarse rhs of the 16x32 coarse points the tile owns = r(2Z,2X) + sum w r(2Z+-1,2X+-1)
+// Algorithmic traffic: b, tx, tz in, x out (32 B/cell) + 4 weights in, 1 rhs out per coarse point.
+constexpr int kDnTZ = 32, kDnTX = 64, kDnFL = 4, kDnFH = 2, kDnThreads = 512;
+constexpr int kDnH = kDnTZ + kDnFL + kDnFH, kDnW = kDnTX + kDnFL + kDnFH;
+constexpr size_t kDnSmem = 4 * (size_t)kDnH * kDnW * sizeof(double);
+static_assert((kDnTZ / 2) * (kDnTX / 2) == kDnThreads, "one coarse point per thread");
+
+__global__ void __launch_bounds__(kDnThreads, 2)
+k_down5(Fine5 v, Weights w, const double *__restrict__ b, double *__restrict__ x, double *__restrict__ bc, int nzc,
+        int nxc, PcgState *st, int init, double *partials, unsigned int *counter)
+{
+    if (stopped(st)) return;
+    constexpr int W = kDnW, H = kDnH, FL = kDnFL, TZ = kDnTZ, TX = kDnTX;
+    LCL_DYNAMIC_SMEM(double, smem);
+    double *sb = smem, *stx = smem + H * W, *stz = smem + 2 * H * W, *sx = smem + 3 * H * W;
+    const int nz = v.nz, nx = v.nx;
+    const int tiles_x = (nx + TX - 1) / TX, tiles_z = (nz + TZ - 1) / TZ;
+    const int tid = threadIdx.x;
+    double acc[2] = {0.0, 0.0};
+    for (long long t = blockIdx.x; t < (long long)tiles_x * tiles_z; t += gridDim.x) {
+        const int z0 = (int)(t / tiles_x) * TZ, x0 = (int)(t % tiles_x) * TX;
+        // ---- stage b, the right face (tx; txl in column -1) and the upper face (tz; tzb in row -1) of every framed cell
+        for (int k = tid; k < H * W; k += kDnThreads) {
+            const int z = z0 + k / W - FL, xx = x0 + k % W - FL;
+            const bool zin = z >= 0 && z < nz, xin = xx >= 0 && xx < nx;
+            const bool in = zin && xin, fx = zin && xx >= -1 && xx < nx, fz = xin && z >= -1 && z < nz;
+            const size_t i = in ? (size_t)z * nx + xx : 0;
+            cp_async8(&sb[k], b + i, in);
+            cp_async8(&stx[k], fx ? (xx >= 0 ? v.tx + i : v.txl + z) : v.tx, fx);
+            cp_async8(&stz[k], fz ? (z >= 0 ? v.tz + i : v.tzb + xx) : v.tz, fz);
         }
-        if (!(tot[0] == tot[0]) || !(tot[1] == tot[1])) st->failed = 1;
-    });
+        // restriction weights of this thread's coarse point ride along
+        const int cl = tid / (TX / 2), cc = tid % (TX / 2);
+        const int Z = z0 / 2 + cl, X = x0 / 2 + cc;
+        double wne = 0.0, wnw = 0.0, wse = 0.0, wsw = 0.0;
+        const bool cin = Z < nzc && X < nxc;
+        if (cin) {
+            const size_t bk = (size_t)Z * nxc + X;
+            const bool xm = X > 0, xp = 2 * X + 1 < nx, zm = Z > 0, zp = 2 * Z + 1 < nz;
+            if (zp && xp) wne = w.csw[bk];
+            if (zp && xm) wnw = w.cse[bk - 1];
+            if (zm && xp) wse = w.cnw[bk - nxc];
+            if (zm && xm) wsw = w.cne[bk - nxc - 1];
+        }
+        cp_async_wait_all();
+        __syncthreads();
+        // ---- red cells ((lz + lx) even; z0, x0 are even), rows -3..TZ+1, columns -3..TX+1
+        {
+            constexpr int R = TZ + 5, NC = (TX + 5 + 1) / 2;
+            for (int k = tid; k < R * NC; k += kDnThreads) {
+                const int lz = k / NC - 3;
+                const int lx = 2 * (k % NC) - 3 + ((lz & 1) ^ 1);
+                if (lx > TX + 1) continue;
+                const int z = z0 + lz, xx = x0 + lx, idx = (lz + FL) * W + lx + FL;
+                double val = 0.0;
+                if (z >= 0 && z < nz && xx >= 0 && xx < nx) {
+                    const double bi = sb[idx];
+                    const double inv = 1.0 / ((stx[idx - 1] + stx[idx]) + (stz[idx - W] + stz[idx]));
+                    val = bi * inv;
+                    if (lz >= 0 && lz < TZ && lx >= 0 && lx < TX) { acc[0] += bi * bi; acc[1] += bi * bi * inv; }
+                }
+                sx[idx] = val;
+            }
+        }
+        __syncthreads();
+        // ---- black cells, rows -2..TZ, columns -2..TX (neighbours outside the grid hold 0)
+        {
+            constexpr int R = TZ + 3, NC = (TX + 3 + 1) / 2;
+            for (int k = tid; k < R * NC; k += kDnThreads) {
+                const int lz = k / NC - 2;
+                const int lx = 2 * (k % NC) - 2 + ((lz & 1) ^ 1);
+                if (lx > TX) continue;
+                const int z = z0 + lz, xx = x0 + lx, idx = (lz + FL) * W + lx + FL;
+                double val = 0.0;
+                if (z >= 0 && z < nz && xx >= 0 && xx < nx) {
+                    const double tl = stx[idx - 1], tr = stx[idx], td = stz[idx - W], tu = stz[idx];
+                    const double bi = sb[idx];
+                    double s = bi;
+                    s += tl * sx[idx - 1];
+                    s += tr * sx[idx + 1];
+                    s += td * sx[idx - W];
+                    s += tu * sx[idx + W];
+                    const double inv = 1.0 / ((tl + tr) + (td + tu));
+                    val = s * inv;
+                    if (lz >= 0 && lz < TZ && lx >= 0 && lx < TX) { acc[0] += bi * bi; acc[1] += bi * bi * inv; }
+                }
+                sx[idx] = val;
+            }
+        }
+        __syncthreads();
+        // ---- residual at red cells, rows -1..TZ-1, columns -1..TX-1, in place over b (it is 0 at black cells)
+        {
+            constexpr int R = TZ + 1, NC = (TX + 1 + 1) / 2;
+            for (int k = tid; k < R * NC; k += kDnThreads) {
+                const int lz = k / NC - 1;
+                const int lx = 2 * (k % NC) - 1 + ((lz & 1) ^ 1);
+                if (lx > TX - 1) continue;
+                const int z = z0 + lz, xx = x0 + lx, idx = (lz + FL) * W + lx + FL;
+                if (z >= 0 && z < nz && xx >= 0 && xx < nx) {
+                    const double xi = sx[idx];
+                    double s = sb[idx];
+                    s -= stx[idx - 1] * (xi - sx[idx - 1]);
+                    s -= stx[idx] * (xi - sx[idx + 1]);
+                    s -= stz[idx - W] * (xi - sx[idx - W]);
+                    s -= stz[idx] * (xi - sx[idx + W]);
+                    sb[idx] = s;
+                }
+            }
+        }
+        // ---- x of the tile, out of place (independent of the residual pass: no barrier needed before it)
+        for (int k = tid; k < TZ * TX / 2; k += kDnThreads) {
+            const int lz = k / (TX / 2), lx = 2 * (k % (TX / 2));
+            const int z = z0 + lz, xe = x0 + lx;
+            if (z >= nz || xe >= nx) continue;
+            const size_t i = (size_t)z * nx + xe;
+            const int idx = (lz + FL) * W + lx + FL;
+            const double v0 = sx[idx], v1 = sx[idx + 1];
+            if (xe + 1 < nx && !(nx & 1)) {
+                *reinterpret_cast<double2 *>(x + i) = make_double2(v0, v1);   // i even when nx even: aligned
+            } else {
+                x[i] = v0;
+                if (xe + 1 < nx) x[i + 1] = v1;
+            }
+        }
+        __syncthreads();
+        if (cin) {
+            const int idx = (2 * cl + FL) * W + 2 * cc + FL;
+            double s = sb[idx];
+            s += wne * sb[idx + W + 1];
+            s += wnw * sb[idx + W - 1];
+            s += wse * sb[idx - W + 1];
+            s += wsw * sb[idx - W - 1];
+            bc[(size_t)Z * nxc + X] = s;
+        }
+        __syncthreads();
+    }
+    grid_sum_finalize<2>(acc, partials, counter, [=](const double(&tot)[2]) { down_norms_finalize(st, init, tot); });
 }
 
 // Fine level, up leg: x += P e, then one EXACT black/red sweep, and b.x (= r.z of PCG) in one launch.
@@ -661,6 +812,19 @@ k_dot_norms(const double *__restrict__ b, const double *__restrict__ x, Fine5 v,
 }
 
 // ------------------------------------------------------------------------------------- driver
+// persistent grid of the fused down leg: two resident blocks per SM
+static int down_grid(Solver &s)
+{
+    if (!s.down_configured) {   // per device: the attribute lives in the context of the solver's GPU
+        CUDA_CHECK(cudaFuncSetAttribute(k_down5, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDnSmem));
+        s.down_configured = true;
+    }
+    const long long tiles = (long long)div_up(s.nx, kDnTX) * div_up(s.nz, kDnTZ);
+    long long cap = (long long)s.num_sms * 2;
+    if (cap > kMaxPartials) cap = kMaxPartials;
+    return (int)(tiles < cap ? tiles : cap);
+}
+
 double bench_launch_cycle(Solver &s, const std::string &name)
 {
     const Fine5 v5 = s.view5();
@@ -690,6 +854,12 @@ double bench_launch_cycle(Solver &s, const std::string &name)
                (const double *)nullptr, f.x, s.nu_coarse, Weights{}, (const double *)nullptr, 0, 0,
                (const PcgState *)s.state);
         return 56.0 * (double)f.n;   // b, C, E, N, NE, NW in; x out (couplings re-read from L1/L2 per sweep)
+    }
+    if (name == "down5" && s.levels.size() > 1 && s.levels[0].w.hw) {
+        Level &c = s.levels[1];
+        LAUNCH(k_down5, down_grid(s), kDnThreads, kDnSmem, s.stream, v5, s.levels[0].w, (const double *)s.r, s.z, c.b, c.nz,
+               c.nx, s.state, 0, part, cnt);
+        return 32.0 * n + (8.0 + 32.0) * (double)c.n;   // b, tx, tz in, x out; 4 weights in + coarse rhs out
     }
     if (name == "restrict_residual0" && s.levels.size() > 1 && s.levels[0].w.hw) {
         Level &c = s.levels[1];
@@ -793,11 +963,10 @@ void mg_vcycle(Solver &s, const double *r, double *ztmp, double *zout, PcgState 
     // the halo), so each level ping-pongs: down leg x -> level.x, up leg result -> level.r (the
     // residual it held has been restricted by then).  Fine level: ztmp after the down leg, zout final;
     // zout doubles as the fine residual buffer in between.
-    LAUNCH(k_smooth5_down, tile_grid(s.nz, s.nx), kSmThreads, 0, s.stream, v5, r, ztmp, st, init, part, cnt);
-    {
+    {   // whole fine down leg: smooth, residual, restriction
         Level &c = s.levels[1];
-        LAUNCH(k_restrict_residual5, grid_for(s, c.nz, c.nx, 8), kBlock, 0, s.stream, v5, s.levels[0].w, r,
-               (const double *)ztmp, c.b, c.nz, c.nx, (const PcgState *)st);
+        LAUNCH(k_down5, down_grid(s), kDnThreads, kDnSmem, s.stream, v5, s.levels[0].w, r, ztmp, c.b, c.nz, c.nx, st, init,
+               part, cnt);
     }
     const Weights now{};
     for (size_t l = 1; l + 1 < nlev; l++) {

@@ -156,6 +156,8 @@ inline cudaError_t cudaStreamCreateWithFlags(cudaStream_t *s, int) { *s = (void 
 inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return 0; }
 inline cudaError_t cudaStreamDestroy(cudaStream_t) { return 0; }
 inline cudaError_t cudaDeviceSynchronize() { return 0; }
+enum { cudaFuncAttributeMaxDynamicSharedMemorySize = 8 };
+template <class F> inline cudaError_t cudaFuncSetAttribute(F, int, int) { return 0; }
 inline cudaError_t cudaEventCreate(cudaEvent_t *e) { *e = new cusimEvent(); return 0; }
 inline cudaError_t cudaEventDestroy(cudaEvent_t e) { delete e; return 0; }
 inline cudaError_t cudaEventRecord(cudaEvent_t e, cudaStream_t) { e->t = std::chrono::steady_clock::now(); return 0; }

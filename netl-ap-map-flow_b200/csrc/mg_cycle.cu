@@ -427,18 +427,26 @@ k_smooth5_down(Fine5 v, const double *__restrict__ b, double *__restrict__ x, Pc
 
 // Fine level, whole down leg in ONE launch: exact red/black sweep from a zero guess, the residual it
 // leaves (non-zero at red cells only) and its restriction to the coarse right-hand side.
-// A block stages b and the faces of a 32x64 tile plus frame in shared memory with asynchronous copies
-// (everything in flight at once, zero-filled outside the grid, so the passes need no bounds logic and
-// touch no global memory), then recomputes the frame instead of exchanging it:
+// A block stages b and the faces of a 26x58 tile plus frame -- 32 rows of 64 -- in shared memory with
+// asynchronous copies (everything in flight at once, zero-filled outside the grid, so the passes need
+// no neighbour logic and touch no global memory), then recomputes the frame instead of exchanging it:
 //   red  (rows -3..TZ+1)  x = b/diag                    -> needs nothing else
 //   black(rows -2..TZ)    x = (b + sum t x_red)/diag    -> exactly what the two-pass version computes
 //   residual at red cells (rows -1..TZ-1), in place over b
-//   coarse rhs of the 16x32 coarse points the tile owns = r(2Z,2X) + sum w r(2Z+-1,2X+-1)
+//   coarse rhs of the 13x29 coarse points the tile owns = r(2Z,2X) + sum w r(2Z+-1,2X+-1)
+// A warp walks rows, its lanes the cells of one colour in the row (32 per framed row): all index
+// arithmetic is shifts and adds, the row tests are warp-uniform.
 // Algorithmic traffic: b, tx, tz in, x out (32 B/cell) + 4 weights in, 1 rhs out per coarse point.
-constexpr int kDnTZ = 32, kDnTX = 64, kDnFL = 4, kDnFH = 2, kDnThreads = 512;
+constexpr int kDnTZ = 26, kDnTX = 58, kDnFL = 4, kDnFH = 2, kDnThreads = 512, kDnWarps = kDnThreads / 32;
 constexpr int kDnH = kDnTZ + kDnFL + kDnFH, kDnW = kDnTX + kDnFL + kDnFH;
 constexpr size_t kDnSmem = 4 * (size_t)kDnH * kDnW * sizeof(double);
-static_assert((kDnTZ / 2) * (kDnTX / 2) == kDnThreads, "one coarse point per thread");
+static_assert(kDnW == 64 && kDnH == 2 * kDnWarps, "a framed row is two lane rounds, the framed tile two warp rounds");
+static_assert(kDnTZ / 2 <= kDnWarps && kDnTX / 2 <= 32, "one coarse point per thread");
+
+// Shared-memory layout of a framed row: the 32 even columns first, then the 32 odd ones, so the lanes
+// of a warp walking one colour (stride 2 in x) touch consecutive doubles -- no bank conflicts -- and so
+// do their left/right neighbours (the other parity) and the rows above and below.
+__device__ __forceinline__ int dn_pos(int row, int col) { return row * kDnW + (col >> 1) + ((col & 1) << 5); }
 
 __global__ void __launch_bounds__(kDnThreads, 2)
 k_down5(Fine5 v, Weights w, const double *__restrict__ b, double *__restrict__ x, double *__restrict__ bc, int nzc,
@@ -450,25 +458,35 @@ k_down5(Fine5 v, Weights w, const double *__restrict__ b, double *__restrict__ x
     double *sb = smem, *stx = smem + H * W, *stz = smem + 2 * H * W, *sx = smem + 3 * H * W;
     const int nz = v.nz, nx = v.nx;
     const int tiles_x = (nx + TX - 1) / TX, tiles_z = (nz + TZ - 1) / TZ;
-    const int tid = threadIdx.x;
+    const int lane = threadIdx.x & 31, wy = threadIdx.x >> 5;
     double acc[2] = {0.0, 0.0};
     for (long long t = blockIdx.x; t < (long long)tiles_x * tiles_z; t += gridDim.x) {
         const int z0 = (int)(t / tiles_x) * TZ, x0 = (int)(t % tiles_x) * TX;
-        // ---- stage b, the right face (tx; txl in column -1) and the upper face (tz; tzb in row -1) of every framed cell
-        for (int k = tid; k < H * W; k += kDnThreads) {
-            const int z = z0 + k / W - FL, xx = x0 + k % W - FL;
-            const bool zin = z >= 0 && z < nz, xin = xx >= 0 && xx < nx;
-            const bool in = zin && xin, fx = zin && xx >= -1 && xx < nx, fz = xin && z >= -1 && z < nz;
-            const size_t i = in ? (size_t)z * nx + xx : 0;
-            cp_async8(&sb[k], b + i, in);
-            cp_async8(&stx[k], fx ? (xx >= 0 ? v.tx + i : v.txl + z) : v.tx, fx);
-            cp_async8(&stz[k], fz ? (z >= 0 ? v.tz + i : v.tzb + xx) : v.tz, fz);
+        // ---- stage b, the right face (tx; txl in column -1) and the upper face (tz; tzb in row -1) of every framed cell.
+        // Lanes 0-15 take the even columns of a 32-column chunk, lanes 16-31 the odd ones: one contiguous
+        // 256-byte read, two conflict-free 128-byte shared-memory writes.
+#pragma unroll
+        for (int row = wy; row < H; row += kDnWarps) {
+            const int z = z0 + row - FL;
+            const bool zin = z >= 0 && z < nz, zface = z >= -1 && z < nz;
+            const size_t zoff = zin ? (size_t)z * nx : 0;
+            const double *brow = b + zoff, *txrow = v.tx + zoff, *tzrow = zin ? v.tz + zoff : v.tzb;
+            const double *txl = v.txl + (zin ? z : 0);
+#pragma unroll
+            for (int c = 0; c < W; c += 32) {
+                const int col = c + 2 * (lane & 15) + (lane >> 4);
+                const int xx = x0 + col - FL, k = dn_pos(row, col);
+                const bool xin = xx >= 0 && xx < nx;
+                const int xs = xin ? xx : 0;
+                cp_async8(&sb[k], brow + xs, zin && xin);
+                cp_async8(&stx[k], xx >= 0 ? txrow + xs : txl, zin && xx >= -1 && xx < nx);
+                cp_async8(&stz[k], tzrow + xs, zface && xin);
+            }
         }
         // restriction weights of this thread's coarse point ride along
-        const int cl = tid / (TX / 2), cc = tid % (TX / 2);
-        const int Z = z0 / 2 + cl, X = x0 / 2 + cc;
+        const int Z = z0 / 2 + wy, X = x0 / 2 + lane;
+        const bool cin = wy < TZ / 2 && lane < TX / 2 && Z < nzc && X < nxc;
         double wne = 0.0, wnw = 0.0, wse = 0.0, wsw = 0.0;
-        const bool cin = Z < nzc && X < nxc;
         if (cin) {
             const size_t bk = (size_t)Z * nxc + X;
             const bool xm = X > 0, xp = 2 * X + 1 < nx, zm = Z > 0, zp = 2 * Z + 1 < nz;
@@ -480,76 +498,70 @@ k_down5(Fine5 v, Weights w, const double *__restrict__ b, double *__restrict__ x
         cp_async_wait_all();
         __syncthreads();
         // ---- red cells ((lz + lx) even; z0, x0 are even), rows -3..TZ+1, columns -3..TX+1
-        {
-            constexpr int R = TZ + 5, NC = (TX + 5 + 1) / 2;
-            for (int k = tid; k < R * NC; k += kDnThreads) {
-                const int lz = k / NC - 3;
-                const int lx = 2 * (k % NC) - 3 + ((lz & 1) ^ 1);
-                if (lx > TX + 1) continue;
-                const int z = z0 + lz, xx = x0 + lx, idx = (lz + FL) * W + lx + FL;
-                double val = 0.0;
-                if (z >= 0 && z < nz && xx >= 0 && xx < nx) {
-                    const double bi = sb[idx];
-                    const double inv = 1.0 / ((stx[idx - 1] + stx[idx]) + (stz[idx - W] + stz[idx]));
-                    val = bi * inv;
-                    if (lz >= 0 && lz < TZ && lx >= 0 && lx < TX) { acc[0] += bi * bi; acc[1] += bi * bi * inv; }
-                }
-                sx[idx] = val;
+#pragma unroll
+        for (int row = wy; row < TZ + 5; row += kDnWarps) {
+            const int lz = row - 3, lx = 2 * lane - 3 + ((lz & 1) ^ 1);
+            if (lx > TX + 1) continue;
+            const int z = z0 + lz, xx = x0 + lx, par = (lx + FL) & 1;
+            const int p = dn_pos(lz + FL, lx + FL), pl = p + (par ? -32 : 31);
+            double val = 0.0;
+            if (z >= 0 && z < nz && xx >= 0 && xx < nx) {
+                const double bi = sb[p];
+                const double inv = 1.0 / ((stx[pl] + stx[p]) + (stz[p - W] + stz[p]));
+                val = bi * inv;
+                if (lz >= 0 && lz < TZ && lx >= 0 && lx < TX) { acc[0] += bi * bi; acc[1] += bi * bi * inv; }
             }
+            sx[p] = val;
         }
         __syncthreads();
         // ---- black cells, rows -2..TZ, columns -2..TX (neighbours outside the grid hold 0)
-        {
-            constexpr int R = TZ + 3, NC = (TX + 3 + 1) / 2;
-            for (int k = tid; k < R * NC; k += kDnThreads) {
-                const int lz = k / NC - 2;
-                const int lx = 2 * (k % NC) - 2 + ((lz & 1) ^ 1);
-                if (lx > TX) continue;
-                const int z = z0 + lz, xx = x0 + lx, idx = (lz + FL) * W + lx + FL;
-                double val = 0.0;
-                if (z >= 0 && z < nz && xx >= 0 && xx < nx) {
-                    const double tl = stx[idx - 1], tr = stx[idx], td = stz[idx - W], tu = stz[idx];
-                    const double bi = sb[idx];
-                    double s = bi;
-                    s += tl * sx[idx - 1];
-                    s += tr * sx[idx + 1];
-                    s += td * sx[idx - W];
-                    s += tu * sx[idx + W];
-                    const double inv = 1.0 / ((tl + tr) + (td + tu));
-                    val = s * inv;
-                    if (lz >= 0 && lz < TZ && lx >= 0 && lx < TX) { acc[0] += bi * bi; acc[1] += bi * bi * inv; }
-                }
-                sx[idx] = val;
+#pragma unroll
+        for (int row = wy; row < TZ + 3; row += kDnWarps) {
+            const int lz = row - 2, lx = 2 * lane - 2 + ((lz & 1) ^ 1);
+            if (lx > TX) continue;
+            const int z = z0 + lz, xx = x0 + lx, par = (lx + FL) & 1;
+            const int p = dn_pos(lz + FL, lx + FL), pl = p + (par ? -32 : 31), pr = p + (par ? -31 : 32);
+            double val = 0.0;
+            if (z >= 0 && z < nz && xx >= 0 && xx < nx) {
+                const double tl = stx[pl], tr = stx[p], td = stz[p - W], tu = stz[p];
+                const double bi = sb[p];
+                double s = bi;
+                s += tl * sx[pl];
+                s += tr * sx[pr];
+                s += td * sx[p - W];
+                s += tu * sx[p + W];
+                const double inv = 1.0 / ((tl + tr) + (td + tu));
+                val = s * inv;
+                if (lz >= 0 && lz < TZ && lx >= 0 && lx < TX) { acc[0] += bi * bi; acc[1] += bi * bi * inv; }
             }
+            sx[p] = val;
         }
         __syncthreads();
         // ---- residual at red cells, rows -1..TZ-1, columns -1..TX-1, in place over b (it is 0 at black cells)
-        {
-            constexpr int R = TZ + 1, NC = (TX + 1 + 1) / 2;
-            for (int k = tid; k < R * NC; k += kDnThreads) {
-                const int lz = k / NC - 1;
-                const int lx = 2 * (k % NC) - 1 + ((lz & 1) ^ 1);
-                if (lx > TX - 1) continue;
-                const int z = z0 + lz, xx = x0 + lx, idx = (lz + FL) * W + lx + FL;
-                if (z >= 0 && z < nz && xx >= 0 && xx < nx) {
-                    const double xi = sx[idx];
-                    double s = sb[idx];
-                    s -= stx[idx - 1] * (xi - sx[idx - 1]);
-                    s -= stx[idx] * (xi - sx[idx + 1]);
-                    s -= stz[idx - W] * (xi - sx[idx - W]);
-                    s -= stz[idx] * (xi - sx[idx + W]);
-                    sb[idx] = s;
-                }
+#pragma unroll
+        for (int row = wy; row < TZ + 1; row += kDnWarps) {
+            const int lz = row - 1, lx = 2 * lane - 1 + ((lz & 1) ^ 1);
+            if (lx > TX - 1) continue;
+            const int z = z0 + lz, xx = x0 + lx, par = (lx + FL) & 1;
+            const int p = dn_pos(lz + FL, lx + FL), pl = p + (par ? -32 : 31), pr = p + (par ? -31 : 32);
+            if (z >= 0 && z < nz && xx >= 0 && xx < nx) {
+                const double xi = sx[p];
+                double s = sb[p];
+                s -= stx[pl] * (xi - sx[pl]);
+                s -= stx[p] * (xi - sx[pr]);
+                s -= stz[p - W] * (xi - sx[p - W]);
+                s -= stz[p] * (xi - sx[p + W]);
+                sb[p] = s;
             }
         }
         // ---- x of the tile, out of place (independent of the residual pass: no barrier needed before it)
-        for (int k = tid; k < TZ * TX / 2; k += kDnThreads) {
-            const int lz = k / (TX / 2), lx = 2 * (k % (TX / 2));
-            const int z = z0 + lz, xe = x0 + lx;
-            if (z >= nz || xe >= nx) continue;
+#pragma unroll
+        for (int lz = wy; lz < TZ; lz += kDnWarps) {
+            const int z = z0 + lz, xe = x0 + 2 * lane;
+            if (lane >= TX / 2 || z >= nz || xe >= nx) continue;
             const size_t i = (size_t)z * nx + xe;
-            const int idx = (lz + FL) * W + lx + FL;
-            const double v0 = sx[idx], v1 = sx[idx + 1];
+            const int p = dn_pos(lz + FL, 2 * lane + FL);      // even column; its right neighbour is at p + 32
+            const double v0 = sx[p], v1 = sx[p + 32];
             if (xe + 1 < nx && !(nx & 1)) {
                 *reinterpret_cast<double2 *>(x + i) = make_double2(v0, v1);   // i even when nx even: aligned
             } else {
@@ -559,12 +571,12 @@ k_down5(Fine5 v, Weights w, const double *__restrict__ b, double *__restrict__ x
         }
         __syncthreads();
         if (cin) {
-            const int idx = (2 * cl + FL) * W + 2 * cc + FL;
-            double s = sb[idx];
-            s += wne * sb[idx + W + 1];
-            s += wnw * sb[idx + W - 1];
-            s += wse * sb[idx - W + 1];
-            s += wsw * sb[idx - W - 1];
+            const int p = dn_pos(2 * wy + FL, 2 * lane + FL);  // even column: left neighbour p + 31, right p + 32
+            double s = sb[p];
+            s += wne * sb[p + W + 32];
+            s += wnw * sb[p + W + 31];
+            s += wse * sb[p - W + 32];
+            s += wsw * sb[p - W + 31];
             bc[(size_t)Z * nxc + X] = s;
         }
         __syncthreads();

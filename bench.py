@@ -318,8 +318,8 @@ def main():
     step_device()
     kern = {}
     # launches per PCG iteration of each fine-level kernel (+ the level-1 kernels of the V-cycle)
-    per_iter = {"spmv": 1, "update": 1, "direction": 1, "down5": 1,
-                "smooth_up": 1, "smooth9_l1": 1, "residual9_l1": 1, "restrict1": 1, "smooth9_l1_up": 1, "vcycle": 1}
+    per_iter = {"spmv": 1, "update": 1, "direction": 1, "down5": 1, "up5": 1,
+                "smooth9_l1": 1, "residual9_l1": 1, "restrict1": 1, "smooth9_l1_up": 1, "vcycle": 1}
     for name in per_iter:
         ms, nbytes = solver.time_kernel(name, reps=20)
         step_device() if name != list(per_iter)[-1] else None

@@ -448,6 +448,35 @@ static_assert(kDnTZ / 2 <= kDnWarps && kDnTX / 2 <= 32, "one coarse point per th
 // do their left/right neighbours (the other parity) and the rows above and below.
 __device__ __forceinline__ int dn_pos(int row, int col) { return row * kDnW + (col >> 1) + ((col & 1) << 5); }
 
+// Stage b, the right face (tx; txl in column -1) and the upper face (tz; tzb in row -1) of every cell
+// of a framed 32x64 tile whose frame is F cells on the low sides, asynchronously and zero-filled
+// outside the grid.  Lanes 0-15 take the even columns of a 32-column chunk, lanes 16-31 the odd ones:
+// one contiguous 256-byte read, two conflict-free 128-byte shared-memory writes.
+template <int F>
+__device__ __forceinline__ void stage_tile5(double *sb, double *stx, double *stz, const Fine5 &v,
+                                            const double *__restrict__ b, int z0, int x0, int wy, int lane)
+{
+    const int nz = v.nz, nx = v.nx;
+#pragma unroll
+    for (int row = wy; row < kDnH; row += kDnWarps) {
+        const int z = z0 + row - F;
+        const bool zin = z >= 0 && z < nz, zface = z >= -1 && z < nz;
+        const size_t zoff = zin ? (size_t)z * nx : 0;
+        const double *brow = b + zoff, *txrow = v.tx + zoff, *tzrow = zin ? v.tz + zoff : v.tzb;
+        const double *txl = v.txl + (zin ? z : 0);
+#pragma unroll
+        for (int c = 0; c < kDnW; c += 32) {
+            const int col = c + 2 * (lane & 15) + (lane >> 4);
+            const int xx = x0 + col - F, k = dn_pos(row, col);
+            const bool xin = xx >= 0 && xx < nx;
+            const int xs = xin ? xx : 0;
+            cp_async8(&sb[k], brow + xs, zin && xin);
+            cp_async8(&stx[k], xx >= 0 ? txrow + xs : txl, zin && xx >= -1 && xx < nx);
+            cp_async8(&stz[k], tzrow + xs, zface && xin);
+        }
+    }
+}
+
 __global__ void __launch_bounds__(kDnThreads, 2)
 k_down5(Fine5 v, Weights w, const double *__restrict__ b, double *__restrict__ x, double *__restrict__ bc, int nzc,
         int nxc, PcgState *st, int init, double *partials, unsigned int *counter)
@@ -462,27 +491,7 @@ k_down5(Fine5 v, Weights w, const double *__restrict__ b, double *__restrict__ x
     double acc[2] = {0.0, 0.0};
     for (long long t = blockIdx.x; t < (long long)tiles_x * tiles_z; t += gridDim.x) {
         const int z0 = (int)(t / tiles_x) * TZ, x0 = (int)(t % tiles_x) * TX;
-        // ---- stage b, the right face (tx; txl in column -1) and the upper face (tz; tzb in row -1) of every framed cell.
-        // Lanes 0-15 take the even columns of a 32-column chunk, lanes 16-31 the odd ones: one contiguous
-        // 256-byte read, two conflict-free 128-byte shared-memory writes.
-#pragma unroll
-        for (int row = wy; row < H; row += kDnWarps) {
-            const int z = z0 + row - FL;
-            const bool zin = z >= 0 && z < nz, zface = z >= -1 && z < nz;
-            const size_t zoff = zin ? (size_t)z * nx : 0;
-            const double *brow = b + zoff, *txrow = v.tx + zoff, *tzrow = zin ? v.tz + zoff : v.tzb;
-            const double *txl = v.txl + (zin ? z : 0);
-#pragma unroll
-            for (int c = 0; c < W; c += 32) {
-                const int col = c + 2 * (lane & 15) + (lane >> 4);
-                const int xx = x0 + col - FL, k = dn_pos(row, col);
-                const bool xin = xx >= 0 && xx < nx;
-                const int xs = xin ? xx : 0;
-                cp_async8(&sb[k], brow + xs, zin && xin);
-                cp_async8(&stx[k], xx >= 0 ? txrow + xs : txl, zin && xx >= -1 && xx < nx);
-                cp_async8(&stz[k], tzrow + xs, zface && xin);
-            }
-        }
+        stage_tile5<FL>(sb, stx, stz, v, b, z0, x0, wy, lane);
         // restriction weights of this thread's coarse point ride along
         const int Z = z0 / 2 + wy, X = x0 / 2 + lane;
         const bool cin = wy < TZ / 2 && lane < TX / 2 && Z < nzc && X < nxc;
@@ -667,6 +676,110 @@ k_smooth5_up(Fine5 v, const double *__restrict__ b, const double *__restrict__ x
     });
 }
 
+// Fine level, whole up leg in ONE launch, staged like k_down5: x += P e, one EXACT black/red sweep and
+// b.x (= r.z of PCG).  28x60 tiles with a 2-cell frame (32 rows of 64): the thread that owns a coarse
+// 2x2 block builds x + P e for it while the asynchronous copies of b and the faces are in flight.
+constexpr int kUpTZ = 28, kUpTX = 60, kUpF = 2;
+static_assert(kUpTZ + 2 * kUpF == kDnH && kUpTX + 2 * kUpF == kDnW, "same framed tile as the down leg");
+
+__global__ void __launch_bounds__(kDnThreads, 2)
+k_up5(Fine5 v, const double *__restrict__ b, const double *__restrict__ xin, double *__restrict__ xout, Weights w,
+      const double *__restrict__ e, int nzc, int nxc, PcgState *st, int init, double *partials, unsigned int *counter)
+{
+    if (stopped(st)) return;
+    constexpr int W = kDnW, H = kDnH, F = kUpF, TZ = kUpTZ, TX = kUpTX;
+    LCL_DYNAMIC_SMEM(double, smem);
+    double *sb = smem, *stx = smem + H * W, *stz = smem + 2 * H * W, *sx = smem + 3 * H * W;
+    const int nz = v.nz, nx = v.nx;
+    const int tiles_x = (nx + TX - 1) / TX, tiles_z = (nz + TZ - 1) / TZ;
+    const int lane = threadIdx.x & 31, wy = threadIdx.x >> 5;
+    double acc[2] = {0.0, 0.0};
+    for (long long t = blockIdx.x; t < (long long)tiles_x * tiles_z; t += gridDim.x) {
+        const int z0 = (int)(t / tiles_x) * TZ, x0 = (int)(t % tiles_x) * TX;
+        stage_tile5<F>(sb, stx, stz, v, b, z0, x0, wy, lane);
+        {   // x + P e of the coarse block (wy, lane) of the framed tile: rows 2wy, 2wy+1, columns 2lane, 2lane+1
+            const int bz = (z0 >> 1) - 1 + wy, bx = (x0 >> 1) - 1 + lane;
+            double v00 = 0.0, v01 = 0.0, v10 = 0.0, v11 = 0.0;
+            if (bz >= 0 && bx >= 0 && bz < nzc && bx < nxc) {
+                const size_t bk = (size_t)bz * nxc + bx;
+                const size_t i = (size_t)(2 * bz) * nx + 2 * bx;
+                const bool Xp = bx + 1 < nxc, Zp = bz + 1 < nzc;
+                const bool xp = 2 * bx + 1 < nx, zp = 2 * bz + 1 < nz;
+                const double e00 = e[bk];
+                const double e01 = Xp ? e[bk + 1] : 0.0;
+                const double e10 = Zp ? e[bk + nxc] : 0.0;
+                const double e11 = (Zp && Xp) ? e[bk + nxc + 1] : 0.0;
+                v00 = xin[i] + e00;
+                if (xp) v01 = xin[i + 1] + (w.hw[bk] * e00 + w.he[bk] * e01);
+                if (zp) v10 = xin[i + nx] + (w.vs[bk] * e00 + w.vn[bk] * e10);
+                if (zp && xp)
+                    v11 = xin[i + nx + 1] + ((w.csw[bk] * e00 + w.cse[bk] * e01) + (w.cnw[bk] * e10 + w.cne[bk] * e11));
+            }
+            const int p = 2 * wy * W + lane;               // dn_pos(2 wy, 2 lane); the odd column sits 32 further
+            sx[p] = v00;
+            sx[p + 32] = v01;
+            sx[p + W] = v10;
+            sx[p + W + 32] = v11;
+        }
+        cp_async_wait_all();
+        __syncthreads();
+        // ---- black cells ((lz + lx) odd) of the tile and its first frame ring, rows -1..TZ, columns -1..TX
+#pragma unroll
+        for (int row = wy; row < TZ + 2; row += kDnWarps) {
+            const int lz = row - 1, lx = 2 * lane - 1 + (lz & 1);
+            if (lx > TX) continue;
+            const int z = z0 + lz, xx = x0 + lx, par = (lx + F) & 1;
+            const int p = dn_pos(lz + F, lx + F), pl = p + (par ? -32 : 31), pr = p + (par ? -31 : 32);
+            if (z >= 0 && z < nz && xx >= 0 && xx < nx) {
+                const double tl = stx[pl], tr = stx[p], td = stz[p - W], tu = stz[p];
+                double s = sb[p];
+                s += tl * sx[pl];
+                s += tr * sx[pr];
+                s += td * sx[p - W];
+                s += tu * sx[p + W];
+                sx[p] = s / ((tl + tr) + (td + tu));
+            }
+        }
+        __syncthreads();
+        // ---- red cells of the tile: each lane owns a horizontal pair (one red cell to update, one black cell
+        // to copy), accumulates b.x over both and writes them out of place
+#pragma unroll
+        for (int lz = wy; lz < TZ; lz += kDnWarps) {
+            const int z = z0 + lz, xe = x0 + 2 * lane;
+            if (lane >= TX / 2 || z >= nz || xe >= nx) continue;
+            const size_t i = (size_t)z * nx + xe;
+            const int pe = dn_pos(lz + F, 2 * lane + F), po = pe + 32;
+            const int r = lz & 1;                          // 0: the even cell is red, 1: the odd cell is red
+            double v0 = sx[pe], v1 = sx[po];
+            if (xe + r < nx) {
+                const int p = r ? po : pe, pl = r ? pe : pe + 31, pr = r ? po - 31 : po;
+                const double tl = stx[pl], tr = stx[p], td = stz[p - W], tu = stz[p];
+                double s = sb[p];
+                s += tl * sx[pl];
+                s += tr * sx[pr];
+                s += td * sx[p - W];
+                s += tu * sx[p + W];
+                const double xn = s / ((tl + tr) + (td + tu));
+                if (r) v1 = xn; else v0 = xn;
+            }
+            acc[0] += sb[pe] * v0;
+            acc[0] += sb[po] * v1;                         // b and x are both 0 beyond the grid
+            if (xe + 1 < nx && !(nx & 1)) {
+                *reinterpret_cast<double2 *>(xout + i) = make_double2(v0, v1);   // i even when nx even: aligned
+            } else {
+                xout[i] = v0;
+                if (xe + 1 < nx) xout[i + 1] = v1;
+            }
+        }
+        __syncthreads();
+    }
+    grid_sum_finalize<2>(acc, partials, counter, [=](const double(&tot)[2]) {
+        st->rz_new = tot[0];
+        st->beta = init ? 0.0 : tot[0] / st->rz;
+        st->rz = tot[0];
+    });
+}
+
 // ------------------------------------------------------------------------------------ transfers
 // bc = P^T r : thread per coarse point gathers its 3x3 fine neighbourhood
 __global__ void __launch_bounds__(kBlock)
@@ -824,18 +937,21 @@ k_dot_norms(const double *__restrict__ b, const double *__restrict__ x, Fine5 v,
 }
 
 // ------------------------------------------------------------------------------------- driver
-// persistent grid of the fused down leg: two resident blocks per SM
-static int down_grid(Solver &s)
+// persistent grids of the fused fine-level legs: two resident blocks per SM
+static int leg_grid(Solver &s, int tz, int tx)
 {
     if (!s.down_configured) {   // per device: the attribute lives in the context of the solver's GPU
         CUDA_CHECK(cudaFuncSetAttribute(k_down5, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDnSmem));
+        CUDA_CHECK(cudaFuncSetAttribute(k_up5, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDnSmem));
         s.down_configured = true;
     }
-    const long long tiles = (long long)div_up(s.nx, kDnTX) * div_up(s.nz, kDnTZ);
+    const long long tiles = (long long)div_up(s.nx, tx) * div_up(s.nz, tz);
     long long cap = (long long)s.num_sms * 2;
     if (cap > kMaxPartials) cap = kMaxPartials;
     return (int)(tiles < cap ? tiles : cap);
 }
+static int down_grid(Solver &s) { return leg_grid(s, kDnTZ, kDnTX); }
+static int up_grid(Solver &s) { return leg_grid(s, kUpTZ, kUpTX); }
 
 double bench_launch_cycle(Solver &s, const std::string &name)
 {
@@ -853,6 +969,12 @@ double bench_launch_cycle(Solver &s, const std::string &name)
     if (name == "smooth_down") {
         LAUNCH(k_smooth5_down, tile_grid(s.nz, s.nx), kSmThreads, 0, s.stream, v5, (const double *)s.r, s.z, s.state, 0, part, cnt);
         return 32.0 * n;   // b, tx, tz in; x out
+    }
+    if (name == "up5" && s.levels.size() > 1 && s.levels[0].w.hw) {
+        Level &c = s.levels[1];
+        LAUNCH(k_up5, up_grid(s), kDnThreads, kDnSmem, s.stream, v5, (const double *)s.r, (const double *)s.z, s.q,
+               s.levels[0].w, (const double *)c.r, c.nz, c.nx, s.state, 0, part + 4 * kMaxPartials, cnt + 1);
+        return 40.0 * n + (8.0 + 64.0) * (double)c.n;   // x, b, tx, tz in; x out; coarse e + 8 weights
     }
     if (name == "smooth_up" && s.levels.size() > 1 && s.levels[0].w.hw) {
         Level &c = s.levels[1];
@@ -1004,7 +1126,7 @@ void mg_vcycle(Solver &s, const double *r, double *ztmp, double *zout, PcgState 
     }
     {
         Level &c = s.levels[1];
-        LAUNCH(k_smooth5_up, tile_grid(s.nz, s.nx), kSmThreads, 0, s.stream, v5, r, (const double *)ztmp, zout, s.levels[0].w,
+        LAUNCH(k_up5, up_grid(s), kDnThreads, kDnSmem, s.stream, v5, r, (const double *)ztmp, zout, s.levels[0].w,
                (const double *)c.r, c.nz, c.nx, st, init, part + 4 * kMaxPartials, cnt + 1);
     }
 }

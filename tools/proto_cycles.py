@@ -39,10 +39,18 @@ if __name__ == "__main__":
     nl = len(mg.A)
     print("levels", nl, [s for s in mg.shape], flush=True)
     variants = [("V", lambda l: 1)]
-    for lo in (1, 2, 3):
-        variants.append((f"W from L{lo}", lambda l, lo=lo: 2 if l >= lo else 1))
-    for lo, hi in ((2, 4), (2, 5), (3, 5), (3, 6), (2, 6)):
-        variants.append((f"W L{lo}..L{hi}", lambda l, lo=lo, hi=hi: 2 if lo <= l <= hi else 1))
+    import os
+    if os.environ.get("PROTO_SET", "a") == "a":
+        for lo in (1, 2, 3):
+            variants.append((f"W from L{lo}", lambda l, lo=lo: 2 if l >= lo else 1))
+        for lo, hi in ((2, 4), (2, 5), (3, 5), (3, 6), (2, 6)):
+            variants.append((f"W L{lo}..L{hi}", lambda l, lo=lo, hi=hi: 2 if lo <= l <= hi else 1))
+    else:
+        for lv in (1, 2, 3, 4):
+            variants.append((f"gamma2 at L{lv} only", lambda l, lv=lv: 2 if l == lv else 1))
+        for lo, hi in ((1, 2), (2, 3), (3, 4), (1, 3)):
+            variants.append((f"W L{lo}..L{hi}", lambda l, lo=lo, hi=hi: 2 if lo <= l <= hi else 1))
+        variants.append(("gamma3 at L2 only", lambda l: 3 if l == 2 else 1))
     for name, g in variants:
         t1 = time.time()
         x, it, fin = pcg(A, b, lambda r: mg.cycle(0, r, None, g), dinv)

@@ -80,6 +80,11 @@ static Solver *solver_new(int device, int nx, int nz)
         mg_allocate(*s);
         if (const char *e = getenv("APM_LCL_NU_L1")) s->nu_coarse = atoi(e);     // tuning knobs
         if (const char *e = getenv("APM_LCL_NU_DEEP")) s->nu_deep = atoi(e);
+        // large maps: levels 3 and 4 are visited twice per cycle (measured: 8192^2 without contact 108 -> 76 ms,
+        // 4096^2 with contact 55 -> 50 ms; below 4096^2 the extra launches cost more than they save)
+        if (s->n >= ((size_t)1 << 24)) { s->w_lo = 3; s->w_hi = 4; }
+        if (const char *e = getenv("APM_LCL_W_LO")) s->w_lo = atoi(e);
+        if (const char *e = getenv("APM_LCL_W_HI")) s->w_hi = atoi(e);
     } catch (...) {
         solver_free(s);
         throw;
@@ -432,6 +437,41 @@ int apm_lcl_solver_device_field(apm_lcl_solver *h, const char *name, double **pt
     else if (n == "tz") p = s.tz;
     else if (n == "txl") { p = s.txl; c = s.nz; }
     else if (n == "tzb") { p = s.tzb; c = s.nx; }
+    else if (n == "nlevels") { p = s.x; c = s.levels.size(); }   // count carries the answer
+    else if (n.size() > 3 && n[0] == 'L' && n.find('.') != std::string::npos) {
+        // diagnostics: "L<l>.<array>" = a stored coarse operator array (C S E N NE NW, l >= 1) or an
+        // interpolation weight array of level l to l+1 (hw he vs vn csw cse cnw cne th tv tc)
+        const size_t dot = n.find('.');
+        const size_t l = (size_t)atoi(n.substr(1, dot - 1).c_str());
+        const std::string arr = n.substr(dot + 1);
+        if (l >= s.levels.size()) throw CudaError{"no such level"};
+        Level &L = s.levels[l];
+        c = L.n;
+        if (arr == "nz") { p = s.x; c = (size_t)L.nz; }
+        else if (arr == "nx") { p = s.x; c = (size_t)L.nx; }
+        else if (arr == "C") p = L.C;
+        else if (arr == "S") p = L.S;
+        else if (arr == "E") p = L.E;
+        else if (arr == "N") p = L.N;
+        else if (arr == "NE") p = L.NE;
+        else if (arr == "NW") p = L.NW;
+        else {
+            if (l + 1 >= s.levels.size()) throw CudaError{"no weights on the coarsest level"};
+            c = s.levels[l + 1].n;
+            if (arr == "hw") p = L.w.hw;
+            else if (arr == "he") p = L.w.he;
+            else if (arr == "vs") p = L.w.vs;
+            else if (arr == "vn") p = L.w.vn;
+            else if (arr == "csw") p = L.w.csw;
+            else if (arr == "cse") p = L.w.cse;
+            else if (arr == "cnw") p = L.w.cnw;
+            else if (arr == "cne") p = L.w.cne;
+            else if (arr == "th") p = L.w.th;
+            else if (arr == "tv") p = L.w.tv;
+            else if (arr == "tc") p = L.w.tc;
+        }
+        if (!p) throw CudaError{"unknown or absent level array"};
+    }
     else throw CudaError{"unknown field name"};
     *ptr = p;
     if (count) *count = c;

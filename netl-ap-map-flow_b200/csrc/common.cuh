@@ -142,6 +142,7 @@ struct Solver {
 #endif
     long long iter_graph_launches = 0;
     int nu_fine = 1, nu_coarse = 2, nu_deep = 2;   // sweeps: fine, level 1, levels >= 2
+    int w_lo = 1, w_hi = 0;                        // levels visited twice per cycle (empty range: V-cycle)
     bool have_solution = false;
     bool down_configured = false;   // k_down5 opted in to >48 KB dynamic shared memory on this device
     apm_lcl_params last_params{};

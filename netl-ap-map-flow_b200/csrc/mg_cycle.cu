@@ -8,6 +8,8 @@
 // 8+2 B, prolongation 8+8+2 B (DESIGN.md lists the fused variants that replace these).
 #include "device_utils.cuh"
 
+#include <functional>
+
 namespace lcl {
 
 enum { GS_PLAIN = 0, GS_FIRST = 1, GS_LAST = 2 };
@@ -1102,28 +1104,41 @@ void mg_vcycle(Solver &s, const double *r, double *ztmp, double *zout, PcgState 
         LAUNCH(k_down5, down_grid(s), kDnThreads, kDnSmem, s.stream, v5, s.levels[0].w, r, ztmp, c.b, c.nz, c.nx, st, init,
                part, cnt);
     }
+    // Levels >= 1: cycle(l) solves level l approximately for the right-hand side in .b, result in .r.
+    // Levels in [w_lo, w_hi] are visited twice (second time from the first result): a W-cycle
+    // truncated to the few mid levels where the V-cycle loses robustness on contact maps, so the
+    // launch-bound tail levels are not revisited exponentially often.  Two steps of a symmetric
+    // stationary iteration are again a symmetric operator, so CG still applies.
     const Weights now{};
-    for (size_t l = 1; l + 1 < nlev; l++) {
-        Level &f = s.levels[l], &c = s.levels[l + 1];
-        LAUNCH((k_smooth9<true, false, true>), tile_grid(f.nz, f.nx), kSmThreads, 0, s.stream, f.view9(), (const double *)f.b,
-               (const double *)nullptr, f.x, l == 1 ? s.nu_coarse : s.nu_deep, now, (const double *)nullptr, 0, 0,
-               (const PcgState *)st);
+    std::function<void(size_t, bool)> cycle = [&](size_t l, bool zero_init) {
+        Level &f = s.levels[l];
+        if (l == nlev - 1) {   // coarsest: dense solve
+            LAUNCH(k_coarse_solve, 1, 64, f.n * sizeof(double), s.stream, s.coarse_inv, s.coarse_scale,
+                   (const double *)f.b, f.r, (int)f.n, st);
+            return;
+        }
+        Level &c = s.levels[l + 1];
+        const int nu = l == 1 ? s.nu_coarse : s.nu_deep;
+        if (zero_init)
+            LAUNCH((k_smooth9<true, false, true>), tile_grid(f.nz, f.nx), kSmThreads, 0, s.stream, f.view9(),
+                   (const double *)f.b, (const double *)nullptr, f.x, nu, now, (const double *)nullptr, 0, 0,
+                   (const PcgState *)st);
+        else
+            LAUNCH((k_smooth9<false, false, true>), tile_grid(f.nz, f.nx), kSmThreads, 0, s.stream, f.view9(),
+                   (const double *)f.b, (const double *)f.r, f.x, nu, now, (const double *)nullptr, 0, 0,
+                   (const PcgState *)st);
         LAUNCH(k_residual9, grid_for(s, f.nz, f.nx, 8), kBlock, 0, s.stream, f.view9(), (const double *)f.b,
                (const double *)f.x, f.r, st);
         LAUNCH(k_restrict, grid_for(s, c.nz, c.nx, 8), kBlock, 0, s.stream, f.w, (const double *)f.r, f.nz, f.nx,
                c.b, c.nz, c.nx, st);
-    }
-    {   // coarsest: dense solve, result in .r like every other level's up-leg result
-        Level &c = s.levels[nlev - 1];
-        LAUNCH(k_coarse_solve, 1, 64, c.n * sizeof(double), s.stream, s.coarse_inv, s.coarse_scale,
-               (const double *)c.b, c.r, (int)c.n, st);
-    }
-    for (size_t l = nlev - 2; l >= 1; l--) {
-        Level &f = s.levels[l], &c = s.levels[l + 1];
-        LAUNCH((k_smooth9<false, true, false>), tile_grid(f.nz, f.nx), kSmThreads, 0, s.stream, f.view9(), (const double *)f.b,
-               (const double *)f.x, f.r, l == 1 ? s.nu_coarse : s.nu_deep, f.w, (const double *)c.r, c.nz, c.nx,
+        cycle(l + 1, true);
+        if ((int)(l + 1) >= s.w_lo && (int)(l + 1) <= s.w_hi && l + 1 < nlev - 1) cycle(l + 1, false);
+        LAUNCH((k_smooth9<false, true, false>), tile_grid(f.nz, f.nx), kSmThreads, 0, s.stream, f.view9(),
+               (const double *)f.b, (const double *)f.x, f.r, nu, f.w, (const double *)c.r, c.nz, c.nx,
                (const PcgState *)st);
-    }
+    };
+    cycle(1, true);
+    if (1 >= s.w_lo && 1 <= s.w_hi && nlev > 2) cycle(1, false);
     {
         Level &c = s.levels[1];
         LAUNCH(k_up5, up_grid(s), kDnThreads, kDnSmem, s.stream, v5, r, (const double *)ztmp, zout, s.levels[0].w,

@@ -144,14 +144,15 @@ APM_LCL_API int apm_lcl_conductance(const apm_lcl_params *p, const double *apert
 
 /* Access to the most recent solve's device-resident state (for roofline benches): returns
  * device pointers owned by the solver, valid until the next solve/destroy.  name: "pressure", "width",
- * "tx", "tz", "txl", "tzb"; diagnostics of the multigrid hierarchy: "nlevels" (answer in *count),
+ * "tx", "tz", "txl", "tzb"; "r" and "q" (scratch: time_kernel("vcycle") computes q = M^-1 r);
+ * diagnostics of the multigrid hierarchy: "nlevels" (answer in *count),
  * "L<l>.nz", "L<l>.nx" (answer in *count), "L<l>.C|S|E|N|NE|NW" (stored 9-point operator of level
  * l >= 1) and "L<l>.hw|he|vs|vn|csw|cse|cnw|cne|th|tv|tc" (interpolation weights level l -> l+1). */
 APM_LCL_API int apm_lcl_solver_device_field(apm_lcl_solver *s, const char *name, double **ptr, size_t *count);
 
 /* Times ONE kernel of the solve on the solver's current state, `reps` back-to-back launches on the
- * solver's stream bracketed by CUDA events.  name: "spmv", "update", "direction", "smooth_down",
- * "smooth_up", "vcycle", "conductance", "flux".  Returns average ms per launch in *ms and the
+ * solver's stream bracketed by CUDA events.  name: "spmv", "update", "direction", "down5", "up5",
+ * "smooth9_l1", "residual9_l1", "restrict1", "smooth9_l1_up", "vcycle", "conductance", "flux".  Returns average ms per launch in *ms and the
  * kernel's algorithmic bytes per launch in *bytes. */
 APM_LCL_API int apm_lcl_solver_time_kernel(apm_lcl_solver *s, const char *name, int reps, double *ms, double *bytes);
 

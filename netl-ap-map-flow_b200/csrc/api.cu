@@ -260,6 +260,7 @@ static void do_solve(Solver &s, const apm_lcl_params &p, const double *aperture,
     CUDA_CHECK(cudaEventElapsedTime(&ms, s.ev[1], s.ev[2])); sc->solve_ms = ms;
     CUDA_CHECK(cudaEventElapsedTime(&ms, s.ev[0], s.ev[4])); sc->total_ms = ms;
     s.have_solution = true;
+    s.have_hierarchy = true;
     s.last_params = p;
     if (!sc->converged) {
         char buf[256];
@@ -437,6 +438,8 @@ int apm_lcl_solver_device_field(apm_lcl_solver *h, const char *name, double **pt
     else if (n == "tz") p = s.tz;
     else if (n == "txl") { p = s.txl; c = s.nz; }
     else if (n == "tzb") { p = s.tzb; c = s.nx; }
+    else if (n == "r") p = s.r;       // PCG scratch vectors: with time_kernel("vcycle") they give z = M^-1 r
+    else if (n == "q") p = s.q;       // (r in, q out), which the symmetry test of the preconditioner uses
     else if (n == "nlevels") { p = s.x; c = s.levels.size(); }   // count carries the answer
     else if (n.size() > 3 && n[0] == 'L' && n.find('.') != std::string::npos) {
         // diagnostics: "L<l>.<array>" = a stored coarse operator array (C S E N NE NW, l >= 1) or an
@@ -484,7 +487,7 @@ int apm_lcl_solver_time_kernel(apm_lcl_solver *h, const char *name, int reps, do
     API_TRY
     if (!h || !h->s || !name || !ms) throw CudaError{"NULL argument"};
     Solver &s = *h->s;
-    if (!s.have_solution) throw CudaError{"time_kernel needs a completed solve (conductances and hierarchy)"};
+    if (!s.have_hierarchy) throw CudaError{"time_kernel needs a completed solve (conductances and hierarchy)"};
     CUDA_CHECK(cudaSetDevice(s.device));
     const std::string n(name);
     if (reps < 1) reps = 1;

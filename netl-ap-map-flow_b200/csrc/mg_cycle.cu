@@ -1,149 +1,23 @@
 // mg_cycle.cu -- one symmetric multigrid V-cycle, z = M^-1 r, the preconditioner of the PCG solve
 // that replaces the reference's direct D4 elimination (D4_SOLVER_MODULE.F:444-617).
 //
-// Fine level: red/black Gauss-Seidel on the matrix-free 5-point operator (faces tx/tz).
-// Coarse levels: four-colour Gauss-Seidel on the stored symmetric 9-point Galerkin operators.
-// Pre-smoothing runs the colours forward, post-smoothing backward, so M is symmetric (CG needs it).
-// Algorithmic bytes per fine cell and launch (f64): colour pass 40 B, residual 40 B, restriction
-// 8+2 B, prolongation 8+8+2 B (DESIGN.md lists the fused variants that replace these).
+// Fine level: exact red/black Gauss-Seidel on the matrix-free 5-point operator (faces tx/tz); the
+// whole down leg (smooth, residual, restriction) is one launch, k_down5, and the whole up leg
+// (prolongation, smooth, r.z) another, k_up5.
+// Coarse levels: four-colour Gauss-Seidel on the stored symmetric 9-point Galerkin operators, all
+// colours and sweeps of a level in one tile kernel (k_smooth9).
+// Pre-smoothing runs the colours forward, post-smoothing backward, so M is symmetric (CG needs it;
+// tests/test_sim_kernels.py and tests/test_gpu_parity.py check <M a, b> == <a, M b>).
+// Algorithmic bytes per launch are stated at each kernel and in DESIGN.md section 5.
 #include "device_utils.cuh"
 
 #include <functional>
 
 namespace lcl {
 
-enum { GS_PLAIN = 0, GS_FIRST = 1, GS_LAST = 2 };
-
 __device__ __forceinline__ bool stopped(const PcgState *st) { return st && (st->converged | st->failed); }
 
-// ---------------------------------------------------------------------------------- fine level
-// One colour of red/black Gauss-Seidel.  MODE FIRST: zero initial guess (other colour := 0) and the
-// norms ||b||^2, b^T D^-1 b of the right-hand side (= PCG residual) ride along.  MODE LAST: b.x rides
-// along (= r.z of PCG).
-template <int MODE>
-__global__ void __launch_bounds__(kBlock)
-k_gs5(Fine5 v, const double *__restrict__ b, double *__restrict__ x, int color, PcgState *st, int init,
-      double *partials, unsigned int *counter)
-{
-    if (stopped(st)) return;
-    const F5 A{v};
-    const int nz = v.nz, nx = v.nx;
-    const Tiles tiles(nz, nx);
-    double acc[2] = {0.0, 0.0};
-    for (long long t = blockIdx.x; t < tiles.ntiles; t += gridDim.x) {
-        int z, xx;
-        tiles.cell(t, z, xx);
-        if (z >= nz || xx >= nx) continue;
-        const size_t i = (size_t)z * nx + xx;
-        const bool mine = ((z + xx) & 1) == color;
-        if (MODE == GS_PLAIN && !mine) continue;
-        const double bi = b[i];
-        if (MODE == GS_FIRST) {
-            const double dg = A.diag(z, xx);
-            acc[0] += bi * bi;
-            acc[1] += bi * bi / dg;
-            x[i] = mine ? bi / dg : 0.0;
-            continue;
-        }
-        double xi;
-        if (mine) {
-            const double tl = A.left(z, xx), tr = A.right(z, xx), td = A.down(z, xx), tu = A.up(z, xx);
-            double s = bi;
-            if (xx > 0) s += tl * x[i - 1];
-            if (xx + 1 < nx) s += tr * x[i + 1];
-            if (z > 0) s += td * x[i - nx];
-            if (z + 1 < nz) s += tu * x[i + nx];
-            xi = s / ((tl + tr) + (td + tu));
-            x[i] = xi;
-        } else {
-            xi = x[i];
-        }
-        if (MODE == GS_LAST) acc[0] += bi * xi;
-    }
-    if (MODE == GS_FIRST) {
-        grid_sum_finalize<2>(acc, partials, counter, [=](const double(&tot)[2]) {
-            st->rr = tot[0];
-            st->rs = tot[1];
-            if (init) {
-                st->bb = tot[0];
-                st->bs = tot[1];
-            } else if (tot[0] <= st->tol2 * st->bb && tot[1] <= st->tol2 * st->bs) {
-                // Residual norms are met.  Keep iterating only while every update still shrinks the
-                // largest pointwise pressure change geometrically: that is how weakly connected cells
-                // (which global norms do not see) reach 1e-6.  If the change grows twice in a row (or after
-                // 12 such extra iterations), what is
-                // left are floating pockets behind ~1e-14-relative leak conductances, which f64 cannot
-                // resolve (DESIGN.md "floating pockets"), so stop.
-                st->res_ok += 1;
-                if ((st->dx <= st->dx_tol && st->dx_prev <= st->dx_tol) || (st->dx > st->dx_prev && st->dx_prev > st->dx_prev2) || st->res_ok > 12)
-                    st->converged = 1;
-            }
-            if (!(tot[0] == tot[0]) || !(tot[1] == tot[1])) st->failed = 1;
-        });
-    }
-    if (MODE == GS_LAST) {
-        grid_sum_finalize<2>(acc, partials, counter, [=](const double(&tot)[2]) {
-            st->rz_new = tot[0];
-            st->beta = init ? 0.0 : tot[0] / st->rz;
-            st->rz = tot[0];
-        });
-    }
-}
-
-__global__ void __launch_bounds__(kBlock)
-k_residual5(Fine5 v, const double *__restrict__ b, const double *__restrict__ x, double *__restrict__ r,
-            const PcgState *st)
-{
-    if (stopped(st)) return;
-    const F5 A{v};
-    const int nz = v.nz, nx = v.nx;
-    const Tiles tiles(nz, nx);
-    for (long long t = blockIdx.x; t < tiles.ntiles; t += gridDim.x) {
-        int z, xx;
-        tiles.cell(t, z, xx);
-        if (z >= nz || xx >= nx) continue;
-        const size_t i = (size_t)z * nx + xx;
-        const double tl = A.left(z, xx), tr = A.right(z, xx), td = A.down(z, xx), tu = A.up(z, xx);
-        const double xi = x[i];
-        // difference form: boundary faces see the homogeneous Dirichlet value 0
-        double s = b[i];
-        s -= tl * (xi - (xx > 0 ? x[i - 1] : 0.0));
-        s -= tr * (xi - (xx + 1 < nx ? x[i + 1] : 0.0));
-        s -= td * (xi - (z > 0 ? x[i - nx] : 0.0));
-        s -= tu * (xi - (z + 1 < nz ? x[i + nx] : 0.0));
-        r[i] = s;
-    }
-}
-
 // -------------------------------------------------------------------------------- coarse levels
-__global__ void __launch_bounds__(kBlock)
-k_gs9(Coarse9 v, const double *__restrict__ b, double *__restrict__ x, int cz, int cx, const PcgState *st)
-{
-    if (stopped(st)) return;
-    const C9 A{v};
-    const int nz = v.nz, nx = v.nx;
-    const int hz = (nz - cz + 1) / 2, hx = (nx - cx + 1) / 2;   // points of this colour
-    const Tiles tiles(hz, hx);
-    for (long long t = blockIdx.x; t < tiles.ntiles; t += gridDim.x) {
-        int a, c;
-        tiles.cell(t, a, c);
-        if (a >= hz || c >= hx) continue;
-        const int z = 2 * a + cz, xx = 2 * c + cx;
-        const size_t i = (size_t)z * nx + xx;
-        double s = b[i];
-#pragma unroll
-        for (int dz = -1; dz <= 1; dz++)
-#pragma unroll
-            for (int dx = -1; dx <= 1; dx++) {
-                if (dz == 0 && dx == 0) continue;
-                const int qz = z + dz, qx = xx + dx;
-                if (qz < 0 || qz >= nz || qx < 0 || qx >= nx) continue;
-                s += A.g(z, xx, dz, dx) * x[(size_t)qz * nx + qx];
-            }
-        x[i] = s / A.diag(z, xx);
-    }
-}
-
 __global__ void __launch_bounds__(kBlock)
 k_residual9(Coarse9 v, const double *__restrict__ b, const double *__restrict__ x, double *__restrict__ r,
             const PcgState *st)
@@ -355,78 +229,6 @@ __device__ __forceinline__ void down_norms_finalize(PcgState *st, int init, cons
     if (!(tot[0] == tot[0]) || !(tot[1] == tot[1])) st->failed = 1;
 }
 
-// Fine level, down leg: one EXACT red/black sweep from a zero guess in one launch.
-// red = b/diag needs no neighbour, so the red values of the halo ring are recomputed from b and the
-// faces instead of being exchanged; black then sees exactly what the two-pass version saw.
-// ||b||^2 and b^T D^-1 b (= the PCG residual norms) ride along.
-__global__ void __launch_bounds__(256)
-k_smooth5_down(Fine5 v, const double *__restrict__ b, double *__restrict__ x, PcgState *st, int init,
-               double *partials, unsigned int *counter)
-{
-    if (stopped(st)) return;
-    const F5 A{v};
-    const int nz = v.nz, nx = v.nx;
-    constexpr int W = kSmTX + 2, H = kSmTZ + 2;
-    __shared__ double sx[H * W];
-    const int tiles_x = (nx + kSmTX - 1) / kSmTX, tiles_z = (nz + kSmTZ - 1) / kSmTZ;
-    const int tid = threadIdx.x;
-    double acc[2] = {0.0, 0.0};
-    for (long long t = blockIdx.x; t < (long long)tiles_x * tiles_z; t += gridDim.x) {
-        const int z0 = (int)(t / tiles_x) * kSmTZ, x0 = (int)(t % tiles_x) * kSmTX;
-        // red pass over tile + halo ring (colour 0 = (z+x) even): lanes walk the red cells only.  From a
-        // zero guess red = b/diag needs no neighbour, so the ring is recomputed instead of exchanged.
-        constexpr int NR = kSmTX / 2 + 1;
-        for (int k = tid; k < H * NR; k += blockDim.x) {   // (fully unrolled it needs 60 registers: slower)
-            const int lz = k / NR - 1, cidx = k % NR;
-            const int z = z0 + lz;
-            const int lx = 2 * cidx - (z & 1);             // x0 is even: (z + x) even  <=>  lx has the parity of z
-            const int xx = x0 + lx;
-            if (z >= 0 && z < nz && xx >= 0 && xx < nx) {
-                const double bi = b[(size_t)z * nx + xx];
-                const double inv = 1.0 / A.diag(z, xx);
-                sx[(lz + 1) * W + lx + 1] = bi * inv;
-                if (lz >= 0 && lz < kSmTZ && lx >= 0 && lx < kSmTX) { acc[0] += bi * bi; acc[1] += bi * bi * inv; }
-            }
-        }
-        __syncthreads();
-        // black pass, tile interior: each lane owns a horizontal pair (one black cell to update, its red
-        // neighbour to copy) and writes both out of place
-        for (int k = tid; k < kSmTZ * kSmTX / 2; k += blockDim.x) {
-            const int lz = k / (kSmTX / 2), lx = 2 * (k % (kSmTX / 2));
-            const int z = z0 + lz, xe = x0 + lx;
-            if (z >= nz || xe >= nx) continue;
-            const size_t i = (size_t)z * nx + xe;
-            const double *p = &sx[(lz + 1) * W + lx + 1];
-            const bool hasO = xe + 1 < nx;
-            const int r = ((z + xe) & 1) ^ 1;             // 0: the even cell is black, 1: the odd cell is black
-            const int xb = xe + r;
-            double v0 = r ? p[0] : 0.0, v1 = r ? 0.0 : (hasO ? p[1] : 0.0);
-            if (xb < nx) {
-                const double *q = p + r;
-                const double tl = A.left(z, xb), tr = A.right(z, xb), td = A.down(z, xb), tu = A.up(z, xb);
-                const double bi = b[i + r];
-                double s = bi;
-                if (xb > 0) s += tl * q[-1];
-                if (xb + 1 < nx) s += tr * q[1];
-                if (z > 0) s += td * q[-W];
-                if (z + 1 < nz) s += tu * q[W];
-                const double inv = 1.0 / ((tl + tr) + (td + tu));
-                acc[0] += bi * bi;
-                acc[1] += bi * bi * inv;
-                if (r) v1 = s * inv; else v0 = s * inv;
-            }
-            if (hasO && !(nx & 1)) {
-                *reinterpret_cast<double2 *>(x + i) = make_double2(v0, v1);   // i even when nx even: aligned
-            } else {
-                x[i] = v0;
-                if (hasO) x[i + 1] = v1;
-            }
-        }
-        __syncthreads();
-    }
-    grid_sum_finalize<2>(acc, partials, counter, [=](const double(&tot)[2]) { down_norms_finalize(st, init, tot); });
-}
-
 // Fine level, whole down leg in ONE launch: exact red/black sweep from a zero guess, the residual it
 // leaves (non-zero at red cells only) and its restriction to the coarse right-hand side.
 // A block stages b and the faces of a 26x58 tile plus frame -- 32 rows of 64 -- in shared memory with
@@ -595,89 +397,6 @@ k_down5(Fine5 v, Weights w, const double *__restrict__ b, double *__restrict__ x
     grid_sum_finalize<2>(acc, partials, counter, [=](const double(&tot)[2]) { down_norms_finalize(st, init, tot); });
 }
 
-// Fine level, up leg: x += P e, then one EXACT black/red sweep, and b.x (= r.z of PCG) in one launch.
-// The tile carries a 2-cell halo of x + P e so the black cells of the first halo ring can be updated
-// redundantly and the red cells of the tile see exactly what the two-pass version saw.
-__global__ void __launch_bounds__(kSmThreads)
-k_smooth5_up(Fine5 v, const double *__restrict__ b, const double *__restrict__ xin, double *__restrict__ xout, Weights w,
-             const double *__restrict__ e, int nzc, int nxc, PcgState *st, int init, double *partials, unsigned int *counter)
-{
-    if (stopped(st)) return;
-    const F5 A{v};
-    const int nz = v.nz, nx = v.nx;
-    constexpr int W = kSmTX + 4, H = kSmTZ + 4;
-    alignas(16) __shared__ double sx[H * W];
-    const int tiles_x = (nx + kSmTX - 1) / kSmTX, tiles_z = (nz + kSmTZ - 1) / kSmTZ;
-    const int tid = threadIdx.x;
-    double acc[2] = {0.0, 0.0};
-    for (long long t = blockIdx.x; t < (long long)tiles_x * tiles_z; t += gridDim.x) {
-        const int z0 = (int)(t / tiles_x) * kSmTZ, x0 = (int)(t % tiles_x) * kSmTX;
-        load_prolonged<H, W>(sx, xin, w, e, nzc, nxc, z0 - 2, x0 - 2, nz, nx);
-        __syncthreads();
-        // black pass over tile + first halo ring: lanes walk the black cells only (33 per framed row)
-        constexpr int H1 = kSmTZ + 2, NB = kSmTX / 2 + 1;
-#pragma unroll
-        for (int k = tid; k < H1 * NB; k += kSmThreads) {
-            const int lz = k / NB - 1, cidx = k % NB;
-            const int z = z0 + lz;
-            const int lx = 2 * cidx - ((z + 1) & 1);      // x0 is even: (z + x) odd  <=>  lx has the parity of z + 1
-            const int xx = x0 + lx;
-            if (z >= 0 && z < nz && xx >= 0 && xx < nx) {
-                const size_t i = (size_t)z * nx + xx;
-                double *p = &sx[(lz + 2) * W + lx + 2];
-                const double tl = A.left(z, xx), tr = A.right(z, xx), td = A.down(z, xx), tu = A.up(z, xx);
-                double s = b[i];
-                if (xx > 0) s += tl * p[-1];
-                if (xx + 1 < nx) s += tr * p[1];
-                if (z > 0) s += td * p[-W];
-                if (z + 1 < nz) s += tu * p[W];
-                p[0] = s / ((tl + tr) + (td + tu));
-            }
-        }
-        __syncthreads();
-        // red pass: each lane owns a horizontal pair (one red cell to update, one black cell to copy),
-        // accumulates b.x over both and writes them out of place
-#pragma unroll
-        for (int k = tid; k < kSmTZ * kSmTX / 2; k += kSmThreads) {
-            const int lz = k / (kSmTX / 2), lx = 2 * (k % (kSmTX / 2));
-            const int z = z0 + lz, xe = x0 + lx;
-            if (z >= nz || xe >= nx) continue;
-            const size_t i = (size_t)z * nx + xe;
-            const double *p = &sx[(lz + 2) * W + lx + 2];
-            const bool hasO = xe + 1 < nx;
-            const int r = (z + xe) & 1;                   // 0: the even cell is red, 1: the odd cell is red
-            const int xr = xe + r;
-            double v0 = p[0], v1 = p[1];
-            if (xr < nx) {
-                const size_t ir = i + r;
-                const double *q = p + r;
-                const double tl = A.left(z, xr), tr = A.right(z, xr), td = A.down(z, xr), tu = A.up(z, xr);
-                double s = b[ir];
-                if (xr > 0) s += tl * q[-1];
-                if (xr + 1 < nx) s += tr * q[1];
-                if (z > 0) s += td * q[-W];
-                if (z + 1 < nz) s += tu * q[W];
-                const double xn = s / ((tl + tr) + (td + tu));
-                if (r) v1 = xn; else v0 = xn;
-            }
-            acc[0] += b[i] * v0;
-            if (hasO) acc[0] += b[i + 1] * v1;
-            if (hasO && !(nx & 1)) {
-                *reinterpret_cast<double2 *>(xout + i) = make_double2(v0, v1);   // i even when nx even: aligned
-            } else {
-                xout[i] = v0;
-                if (hasO) xout[i + 1] = v1;
-            }
-        }
-        __syncthreads();
-    }
-    grid_sum_finalize<2>(acc, partials, counter, [=](const double(&tot)[2]) {
-        st->rz_new = tot[0];
-        st->beta = init ? 0.0 : tot[0] / st->rz;
-        st->rz = tot[0];
-    });
-}
-
 // Fine level, whole up leg in ONE launch, staged like k_down5: x += P e, one EXACT black/red sweep and
 // b.x (= r.z of PCG).  28x60 tiles with a 2-cell frame (32 rows of 64): the thread that owns a coarse
 // 2x2 block builds x + P e for it while the asynchronous copies of b and the faces are in flight.
@@ -811,80 +530,6 @@ k_restrict(Weights w, const double *__restrict__ r, int nz, int nx, double *__re
     }
 }
 
-// Fine level: residual and restriction in one pass, bc = P^T (b - A x), without storing the residual.
-// After the red/black pre-smoothing sweep the residual of every BLACK cell is zero (they were solved
-// last), and in the 3x3 neighbourhood of a coarse point (even z, even x) the four edge cells are
-// exactly the black ones: only the coarse cell itself and its four diagonal (centre-type) cells
-// contribute.  Their residuals are evaluated in difference form from x and the faces.
-__device__ __forceinline__ double residual5_at(const F5 &A, const double *__restrict__ b, const double *__restrict__ x,
-                                               int z, int xx, int nz, int nx)
-{
-    const size_t i = (size_t)z * nx + xx;
-    const double xi = x[i];
-    double s = b[i];
-    s -= A.left(z, xx) * (xi - (xx > 0 ? x[i - 1] : 0.0));
-    s -= A.right(z, xx) * (xi - (xx + 1 < nx ? x[i + 1] : 0.0));
-    s -= A.down(z, xx) * (xi - (z > 0 ? x[i - nx] : 0.0));
-    s -= A.up(z, xx) * (xi - (z + 1 < nz ? x[i + nx] : 0.0));
-    return s;
-}
-
-__global__ void __launch_bounds__(kBlock)
-k_restrict_residual5(Fine5 v, Weights w, const double *__restrict__ b, const double *__restrict__ x,
-                     double *__restrict__ bc, int nzc, int nxc, const PcgState *st)
-{
-    if (stopped(st)) return;
-    const F5 A{v};
-    const int nz = v.nz, nx = v.nx;
-    const Tiles tiles(nzc, nxc);
-    for (long long t = blockIdx.x; t < tiles.ntiles; t += gridDim.x) {
-        int Z, X;
-        tiles.cell(t, Z, X);
-        if (Z >= nzc || X >= nxc) continue;
-        const int z = 2 * Z, xx = 2 * X;
-        const size_t bk = (size_t)Z * nxc + X;
-        const bool xm = X > 0, xp = xx + 1 < nx, zm = Z > 0, zp = z + 1 < nz;
-        // branch-free: absent diagonal centres are evaluated at a clamped (existing) cell with weight 0,
-        // so the ~50 loads of the five residuals are independent and can all be in flight together
-        const int zu = zp ? z + 1 : z, zd = zm ? z - 1 : z, xr = xp ? xx + 1 : xx, xl = xm ? xx - 1 : xx;
-        const double wne = (zp && xp) ? w.csw[bk] : 0.0, wnw = (zp && xm) ? w.cse[bk - 1] : 0.0;
-        const double wse = (zm && xp) ? w.cnw[bk - nxc] : 0.0, wsw = (zm && xm) ? w.cne[bk - nxc - 1] : 0.0;
-        double s = residual5_at(A, b, x, z, xx, nz, nx);
-        s += wne * residual5_at(A, b, x, zu, xr, nz, nx);
-        s += wnw * residual5_at(A, b, x, zu, xl, nz, nx);
-        s += wse * residual5_at(A, b, x, zd, xr, nz, nx);
-        s += wsw * residual5_at(A, b, x, zd, xl, nz, nx);
-        bc[bk] = s;
-    }
-}
-
-// x += P e : thread per coarse block writes its (up to) four fine points
-__global__ void __launch_bounds__(kBlock)
-k_prolong_add(Weights w, const double *__restrict__ e, int nzc, int nxc, double *__restrict__ x, int nz, int nx,
-              const PcgState *st)
-{
-    if (stopped(st)) return;
-    const Tiles tiles(nzc, nxc);
-    for (long long t = blockIdx.x; t < tiles.ntiles; t += gridDim.x) {
-        int Z, X;
-        tiles.cell(t, Z, X);
-        if (Z >= nzc || X >= nxc) continue;
-        const int z = 2 * Z, xx = 2 * X;
-        const size_t b = (size_t)Z * nxc + X;
-        const size_t i = (size_t)z * nx + xx;
-        const bool xp = xx + 1 < nx, zp = z + 1 < nz;
-        const bool Xp = X + 1 < nxc, Zp = Z + 1 < nzc;
-        const double e00 = e[b];
-        const double e01 = Xp ? e[b + 1] : 0.0;
-        const double e10 = Zp ? e[b + nxc] : 0.0;
-        const double e11 = (Zp && Xp) ? e[b + nxc + 1] : 0.0;
-        x[i] += e00;
-        if (xp) x[i + 1] += w.hw[b] * e00 + w.he[b] * e01;
-        if (zp) x[i + nx] += w.vs[b] * e00 + w.vn[b] * e10;
-        if (zp && xp) x[i + nx + 1] += (w.csw[b] * e00 + w.cse[b] * e01) + (w.cnw[b] * e10 + w.cne[b] * e11);
-    }
-}
-
 // x = S inv S b on the coarsest level (one CTA)
 __global__ void k_coarse_solve(const double *__restrict__ inv, const double *__restrict__ scale,
                                const double *__restrict__ b, double *__restrict__ x, int n, const PcgState *st)
@@ -958,7 +603,6 @@ static int up_grid(Solver &s) { return leg_grid(s, kUpTZ, kUpTX); }
 double bench_launch_cycle(Solver &s, const std::string &name)
 {
     const Fine5 v5 = s.view5();
-    const int g0 = grid_for(s, s.nz, s.nx, 8);
     double *part = s.red + 16 * kMaxPartials;
     unsigned int *cnt = s.red_counters + 4;
     const double n = (double)s.n;
@@ -968,19 +612,9 @@ double bench_launch_cycle(Solver &s, const std::string &name)
         if (cap > kMaxPartials) cap = kMaxPartials;
         return (int)(tiles < cap ? tiles : cap);
     };
-    if (name == "smooth_down") {
-        LAUNCH(k_smooth5_down, tile_grid(s.nz, s.nx), kSmThreads, 0, s.stream, v5, (const double *)s.r, s.z, s.state, 0, part, cnt);
-        return 32.0 * n;   // b, tx, tz in; x out
-    }
     if (name == "up5" && s.levels.size() > 1 && s.levels[0].w.hw) {
         Level &c = s.levels[1];
         LAUNCH(k_up5, up_grid(s), kDnThreads, kDnSmem, s.stream, v5, (const double *)s.r, (const double *)s.z, s.q,
-               s.levels[0].w, (const double *)c.r, c.nz, c.nx, s.state, 0, part + 4 * kMaxPartials, cnt + 1);
-        return 40.0 * n + (8.0 + 64.0) * (double)c.n;   // x, b, tx, tz in; x out; coarse e + 8 weights
-    }
-    if (name == "smooth_up" && s.levels.size() > 1 && s.levels[0].w.hw) {
-        Level &c = s.levels[1];
-        LAUNCH(k_smooth5_up, tile_grid(s.nz, s.nx), kSmThreads, 0, s.stream, v5, (const double *)s.r, (const double *)s.z, s.q,
                s.levels[0].w, (const double *)c.r, c.nz, c.nx, s.state, 0, part + 4 * kMaxPartials, cnt + 1);
         return 40.0 * n + (8.0 + 64.0) * (double)c.n;   // x, b, tx, tz in; x out; coarse e + 8 weights
     }
@@ -996,12 +630,6 @@ double bench_launch_cycle(Solver &s, const std::string &name)
         LAUNCH(k_down5, down_grid(s), kDnThreads, kDnSmem, s.stream, v5, s.levels[0].w, (const double *)s.r, s.z, c.b, c.nz,
                c.nx, s.state, 0, part, cnt);
         return 32.0 * n + (8.0 + 32.0) * (double)c.n;   // b, tx, tz in, x out; 4 weights in + coarse rhs out
-    }
-    if (name == "restrict_residual0" && s.levels.size() > 1 && s.levels[0].w.hw) {
-        Level &c = s.levels[1];
-        LAUNCH(k_restrict_residual5, grid_for(s, c.nz, c.nx, 8), kBlock, 0, s.stream, v5, s.levels[0].w,
-               (const double *)s.r, (const double *)s.z, c.b, c.nz, c.nx, (const PcgState *)s.state);
-        return 32.0 * n + (8.0 + 32.0) * (double)c.n;   // b, x, tx, tz in; 4 weights in + coarse rhs out
     }
     if (name == "smooth9_l1_up" && s.levels.size() > 2) {
         Level &f = s.levels[1], &c = s.levels[2];
@@ -1021,56 +649,11 @@ double bench_launch_cycle(Solver &s, const std::string &name)
                c.b, c.nz, c.nx, s.state);
         return 8.0 * (double)f.n + 72.0 * (double)c.n;
     }
-    if (name == "gs5_first") {
-        LAUNCH((k_gs5<GS_FIRST>), g0, kBlock, 0, s.stream, v5, (const double *)s.r, s.z, 0, s.state, 0, part, cnt);
-        return 32.0 * n;   // b, tx, tz in; x out
-    }
-    if (name == "gs5_color") {
-        LAUNCH((k_gs5<GS_PLAIN>), g0, kBlock, 0, s.stream, v5, (const double *)s.r, s.z, 1, s.state, 0, part, cnt);
-        return 40.0 * n;   // b, x, tx, tz in; x out (whole lines move although one colour is updated)
-    }
-    if (name == "gs5_last") {
-        LAUNCH((k_gs5<GS_LAST>), g0, kBlock, 0, s.stream, v5, (const double *)s.r, s.z, 0, s.state, 0,
-               part + 4 * kMaxPartials, cnt + 1);
-        return 40.0 * n;
-    }
-    if (name == "residual5") {
-        LAUNCH(k_residual5, g0, kBlock, 0, s.stream, v5, (const double *)s.r, (const double *)s.z, s.q, s.state);
-        return 40.0 * n;
-    }
-    if (s.levels.size() > 1 && s.levels[0].w.hw) {
-        Level &c = s.levels[1];
-        if (name == "restrict0") {
-            LAUNCH(k_restrict, grid_for(s, c.nz, c.nx, 8), kBlock, 0, s.stream, s.levels[0].w, (const double *)s.q,
-                   s.nz, s.nx, c.b, c.nz, c.nx, s.state);
-            return 8.0 * n + (8.0 + 64.0) * (double)c.n;   // r in; 8 weights in, coarse rhs out
-        }
-        if (name == "prolong0") {
-            LAUNCH(k_prolong_add, grid_for(s, c.nz, c.nx, 8), kBlock, 0, s.stream, s.levels[0].w, (const double *)c.x,
-                   c.nz, c.nx, s.z, s.nz, s.nx, s.state);
-            return 16.0 * n + (8.0 + 64.0) * (double)c.n;
-        }
-    }
     if (name == "vcycle") {
         mg_vcycle(s, s.r, s.z, s.q, s.state, false);
         return 0.0;
     }
     return -1.0;
-}
-
-static const int kColorZ[4] = {0, 0, 1, 1}, kColorX[4] = {0, 1, 0, 1};
-
-static void smooth9(Solver &s, Level &l, bool forward, int sweeps, PcgState *st)
-{
-    const Coarse9 v = l.view9();
-    for (int k = 0; k < sweeps; k++)
-        for (int c = 0; c < 4; c++) {
-            const int col = forward ? c : 3 - c;
-            const int cz = kColorZ[col], cx = kColorX[col];
-            const int hz = (l.nz - cz + 1) / 2, hx = (l.nx - cx + 1) / 2;
-            if (hz <= 0 || hx <= 0) continue;
-            LAUNCH(k_gs9, grid_for(s, hz, hx, 8), kBlock, 0, s.stream, v, l.b, l.x, cz, cx, st);
-        }
 }
 
 void mg_vcycle(Solver &s, const double *r, double *ztmp, double *zout, PcgState *st, bool init_flag)

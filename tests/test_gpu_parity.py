@@ -150,7 +150,7 @@ def test_full_size_properties_2048(n, contact):
     q_in, q_out = _inflow_outflow(f, 1000.0, 0.0, trz)
     assert q_in == pytest.approx(q_out, rel=1e-7)
     assert abs(s["flow"]) == pytest.approx(q_out, rel=1e-6)
-    assert s["iterations"] < 60
+    assert s["iterations"] < (20 if contact == 0.0 else 40)   # 11 and 27 measured: a weaker cycle shows here first
 
 
 def test_torch_cuda_tensor_io_matches_host_io():
@@ -178,3 +178,56 @@ def test_bulk_solve_matches_single_solves():
     # affine in the boundary pressures: flow scales with (P_in - P_out) on the same map
     q0, q1 = res[0][1]["flow"], res[1][1]["flow"]
     assert q1 / q0 == pytest.approx(750.0 / 1000.0, rel=1e-6)
+
+
+def _device_vector(solver, name):
+    import ctypes as C
+    ptr, cnt = C.c_void_p(), C.c_size_t()
+    assert solver.lib.apm_lcl_solver_device_field(solver._h, name.encode(), C.byref(ptr), C.byref(cnt)) == 0
+    return ptr.value, cnt.value
+
+
+def _memcpy(dst, src, nbytes, kind):
+    try:
+        from cuda.bindings import runtime as cudart
+    except ImportError:                                    # older cuda-python layout
+        from cuda import cudart
+    kinds = cudart.cudaMemcpyKind
+    (err,) = cudart.cudaMemcpy(dst, src, nbytes, getattr(kinds, kind))
+    assert int(err) == 0
+
+
+def _from_device(ptr, count):
+    out = np.empty(count)
+    _memcpy(out.ctypes.data, ptr, out.nbytes, "cudaMemcpyDeviceToHost")
+    return out
+
+
+@pytest.mark.parametrize("w_levels", [None, (1, 2)])
+def test_preconditioner_is_symmetric_positive_on_device(monkeypatch, w_levels):
+    """CG needs M = M^T > 0: <M a, b> == <a, M b> for the cycle the device runs (fused down/up legs,
+    hybrid tile smoothers, truncated W-cycle), on a map that spans many tiles with ragged edges."""
+    if w_levels:
+        monkeypatch.setenv("APM_LCL_W_LO", str(w_levels[0]))
+        monkeypatch.setenv("APM_LCL_W_HI", str(w_levels[1]))
+    nz, nx = 1100, 900
+    a = synth_aperture(nz, nx, seed=5, sigma_c=8, contact=0.2, sigma_k=16)
+    with lcl.LclSolver(nx, nz) as solver:
+        solver.solve(synth_params(), a, fields=("pressure",))
+        tx = _from_device(*_device_vector(solver, "tx")).reshape(nz, nx)
+        tz = _from_device(*_device_vector(solver, "tz")).reshape(nz, nx)
+        txl, tzb = _from_device(*_device_vector(solver, "txl")), _from_device(*_device_vector(solver, "tzb"))
+        diag = (np.concatenate([txl[:, None], tx[:, :-1]], axis=1) + tx) + (np.concatenate([tzb[None, :], tz[:-1]], axis=0) + tz)
+        (r_ptr, n), (q_ptr, _) = _device_vector(solver, "r"), _device_vector(solver, "q")
+        rng = np.random.default_rng(1)
+        va, vb = (diag * rng.standard_normal((nz, nx))).ravel(), (diag * rng.standard_normal((nz, nx))).ravel()
+
+        def apply(v):
+            v = np.ascontiguousarray(v)
+            _memcpy(r_ptr, v.ctypes.data, v.nbytes, "cudaMemcpyHostToDevice")
+            solver.time_kernel("vcycle", reps=1)
+            return _from_device(q_ptr, n)
+        ma, mb = apply(va), apply(vb)
+    aa, bb, ab, ba = ma @ va, mb @ vb, ma @ vb, mb @ va
+    assert aa > 0 and bb > 0
+    assert abs(ab - ba) <= 1e-10 * np.sqrt(aa * bb)

@@ -93,3 +93,41 @@ def test_sim_invalid_boundary_conditions_fail(sim):
         lcl.lcl_solve(params(inlet_rate=1e-9), a, lib=sim)          # both pressures and a rate
     with pytest.raises(lcl._lib.LclError):
         lcl.lcl_solve(params(viscosity=-1.0), a, lib=sim)
+
+
+def _solver_vector(solver, name):
+    import ctypes as C
+    ptr, cnt = C.c_void_p(), C.c_size_t()
+    assert solver.lib.apm_lcl_solver_device_field(solver._h, name.encode(), C.byref(ptr), C.byref(cnt)) == 0
+    return np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_double)), shape=(cnt.value,))   # sim: host memory
+
+
+@pytest.mark.parametrize("w_levels", [None, (1, 2)])
+def test_sim_preconditioner_is_symmetric_positive(sim, monkeypatch, w_levels):
+    """CG needs M = M^T > 0.  The cycle is assembled from fused, tile-local kernels (down leg, up leg,
+    hybrid 9-point smoothers, optionally the truncated W-cycle): apply it to two vectors through the
+    solver's scratch arrays and compare <M a, b> with <a, M b>.  170 x 150 spans several tiles of every
+    kernel in both directions, with ragged edges."""
+    if w_levels:
+        monkeypatch.setenv("APM_LCL_W_LO", str(w_levels[0]))
+        monkeypatch.setenv("APM_LCL_W_HI", str(w_levels[1]))
+    nz, nx = 170, 150
+    a = synth_aperture(nz, nx, seed=5, sigma_c=4, contact=0.2, sigma_k=6)
+    p = params(viscosity=1e-3, voxel_size=1e-5, avg_factor=1.0)
+    with lcl.LclSolver(nx, nz, lib=sim) as solver:
+        solver.solve(p, a, fields=("pressure",))
+        tx, tz = _solver_vector(solver, "tx").reshape(nz, nx), _solver_vector(solver, "tz").reshape(nz, nx)
+        txl, tzb = _solver_vector(solver, "txl"), _solver_vector(solver, "tzb")
+        diag = (np.concatenate([txl[:, None], tx[:, :-1]], axis=1) + tx) + (np.concatenate([tzb[None, :], tz[:-1]], axis=0) + tz)
+        r, q = _solver_vector(solver, "r"), _solver_vector(solver, "q")
+        rng = np.random.default_rng(1)
+        va, vb = (diag * rng.standard_normal((nz, nx))).ravel(), (diag * rng.standard_normal((nz, nx))).ravel()
+
+        def apply(v):
+            r[:] = v
+            solver.time_kernel("vcycle", reps=1)
+            return q.copy()
+        ma, mb = apply(va), apply(vb)
+    aa, bb, ab, ba = ma @ va, mb @ vb, ma @ vb, mb @ va
+    assert aa > 0 and bb > 0
+    assert abs(ab - ba) <= 1e-10 * np.sqrt(aa * bb)

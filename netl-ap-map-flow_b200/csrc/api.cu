@@ -80,6 +80,7 @@ static Solver *solver_new(int device, int nx, int nz)
         mg_allocate(*s);
         if (const char *e = getenv("APM_LCL_NU_L1")) s->nu_coarse = atoi(e);     // tuning knobs
         if (const char *e = getenv("APM_LCL_NU_DEEP")) s->nu_deep = atoi(e);
+        s->tail.nu = s->tail_top == 1 ? s->nu_coarse : s->nu_deep;
         // large maps: levels 3 and 4 are visited twice per cycle (measured: 8192^2 without contact 108 -> 76 ms,
         // 4096^2 with contact 55 -> 50 ms; below 4096^2 the extra launches cost more than they save)
         if (s->n >= ((size_t)1 << 24)) { s->w_lo = 3; s->w_hi = 4; }

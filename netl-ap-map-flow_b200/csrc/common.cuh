@@ -118,6 +118,21 @@ struct Reducer {
 
 // ---------------------------------------------------------------------------------------------
 // the solver object behind apm_lcl_solver
+// The small levels of the hierarchy (<= kTailCells cells each) are cycled by ONE block in one launch
+// (k_tail_cycle): by value, so the kernel needs no indirection to find its arrays.
+constexpr int kTailMaxLevels = 8, kTailCells = 1024, kTailThreads = 1024;
+struct TailLevel {
+    Coarse9 op;
+    Weights w;            // to the next coarser level (unused on the last)
+    double *x, *b, *r;
+};
+struct TailArgs {
+    TailLevel lv[kTailMaxLevels];
+    int nlev = 0;
+    const double *inv = nullptr, *scale = nullptr;   // dense inverse of the last level
+    int nu = 2;
+};
+
 struct Solver {
     int device = 0, nx = 0, nz = 0;
     size_t n = 0;
@@ -142,6 +157,8 @@ struct Solver {
 #endif
     long long iter_graph_launches = 0;
     int nu_fine = 1, nu_coarse = 2, nu_deep = 2;   // sweeps: fine, level 1, levels >= 2
+    int tail_top = -1;                             // first level cycled by k_tail_cycle (-1: none)
+    TailArgs tail{};
     int w_lo = 1, w_hi = 0;                        // levels visited twice per cycle (empty range: V-cycle)
     bool have_solution = false;    // x holds the pressure of the last solve
     bool have_hierarchy = false;   // conductances and multigrid operators of the last solve are in place

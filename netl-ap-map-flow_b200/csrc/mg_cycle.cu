@@ -530,6 +530,130 @@ k_restrict(Weights w, const double *__restrict__ r, int nz, int nx, double *__re
     }
 }
 
+// ------------------------------------------------------------------------------- the tail levels
+// One colour of Gauss-Seidel on a whole (small) level, in place, by one block.
+__device__ __forceinline__ void tail_gs_colour(const C9 &A, const double *b, double *x, int cz, int cx)
+{
+    const int nz = A.nz(), nx = A.nx();
+    const int hz = (nz - cz + 1) / 2, hx = (nx - cx + 1) / 2;
+    for (int k = threadIdx.x; k < hz * hx; k += blockDim.x) {
+        const int z = 2 * (k / hx) + cz, xx = 2 * (k % hx) + cx;
+        const int i = z * nx + xx;
+        double s = b[i];
+#pragma unroll
+        for (int dz = -1; dz <= 1; dz++)
+#pragma unroll
+            for (int dx = -1; dx <= 1; dx++) {
+                if (dz == 0 && dx == 0) continue;
+                const int qz = z + dz, qx = xx + dx;
+                if (qz < 0 || qz >= nz || qx < 0 || qx >= nx) continue;
+                s += A.g(z, xx, dz, dx) * x[qz * nx + qx];
+            }
+        x[i] = s / A.diag(z, xx);
+    }
+}
+
+// All levels of at most kTailCells cells -- 32x32 and below -- in ONE launch by ONE block: the whole
+// sub-cycle (pre-smoothing, residual, restriction, ..., dense solve, ..., prolongation, post-smoothing)
+// with block barriers where the per-level kernels had launch boundaries.  These levels hold a few
+// hundred cells: their cost was pure launch latency (about 16 launches per visit, several visits per
+// cycle with the W-levels above them).  Here a level is one tile, so the smoother is exact four-colour
+// Gauss-Seidel, backward on the way up: the cycle stays symmetric.
+// rhs in lv[0].b; result in lv[0].r (zero_init == 0: lv[0].r is the initial guess).
+__global__ void __launch_bounds__(kTailThreads)
+k_tail_cycle(TailArgs a, int zero_init, const PcgState *st)
+{
+    if (stopped(st)) return;
+    const int tid = threadIdx.x, T = blockDim.x;
+    __shared__ double sb[64];
+    // (Measured: staging the ~130 KB these levels need in shared memory first is slower than reading
+    // them through L1/L2 phase by phase -- 4.09 vs 3.76 ms for a 1024^2 solve.)
+    for (int l = 0; l + 1 < a.nlev; l++) {
+        const TailLevel &L = a.lv[l], &Cc = a.lv[l + 1];
+        const C9 A{L.op};
+        const int nz = L.op.nz, nx = L.op.nx, n = nz * nx, nzc = Cc.op.nz, nxc = Cc.op.nx;
+        for (int i = tid; i < n; i += T) L.x[i] = (l > 0 || zero_init) ? 0.0 : L.r[i];
+        __syncthreads();
+        for (int sweep = 0; sweep < a.nu; sweep++)
+            for (int col = 0; col < 4; col++) {
+                tail_gs_colour(A, L.b, L.x, col >> 1, col & 1);
+                __syncthreads();
+            }
+        for (int i = tid; i < n; i += T) {   // residual, difference form
+            const int z = i / nx, xx = i % nx;
+            const double xi = L.x[i];
+            double s = L.b[i] - A.S(z, xx) * xi;
+#pragma unroll
+            for (int dz = -1; dz <= 1; dz++)
+#pragma unroll
+                for (int dx = -1; dx <= 1; dx++) {
+                    if (dz == 0 && dx == 0) continue;
+                    const int qz = z + dz, qx = xx + dx;
+                    if (qz < 0 || qz >= nz || qx < 0 || qx >= nx) continue;
+                    s -= A.g(z, xx, dz, dx) * (xi - L.x[qz * nx + qx]);
+                }
+            L.r[i] = s;
+        }
+        __syncthreads();
+        for (int k = tid; k < nzc * nxc; k += T) {   // restriction, as k_restrict
+            const int Z = k / nxc, X = k % nxc;
+            const int z = 2 * Z, x = 2 * X, i = z * nx + x;
+            const bool xm = X > 0, xp = x + 1 < nx, zm = Z > 0, zp = z + 1 < nz;
+            const double *r = L.r;
+            double s = r[i];
+            if (xp) s += L.w.hw[k] * r[i + 1];
+            if (xm) s += L.w.he[k - 1] * r[i - 1];
+            if (zp) s += L.w.vs[k] * r[i + nx];
+            if (zm) s += L.w.vn[k - nxc] * r[i - nx];
+            if (zp && xp) s += L.w.csw[k] * r[i + nx + 1];
+            if (zp && xm) s += L.w.cse[k - 1] * r[i + nx - 1];
+            if (zm && xp) s += L.w.cnw[k - nxc] * r[i - nx + 1];
+            if (zm && xm) s += L.w.cne[k - nxc - 1] * r[i - nx - 1];
+            Cc.b[k] = s;
+        }
+        __syncthreads();
+    }
+    {   // last level: x = S inv S b
+        const TailLevel &L = a.lv[a.nlev - 1];
+        const int n = L.op.nz * L.op.nx;
+        for (int i = tid; i < n; i += T) sb[i] = a.scale[i] * L.b[i];
+        __syncthreads();
+        for (int i = tid; i < n; i += T) {
+            double s = 0.0;
+            for (int j = 0; j < n; j++) s += a.inv[i * n + j] * sb[j];
+            L.r[i] = a.scale[i] * s;
+        }
+        __syncthreads();
+    }
+    for (int l = a.nlev - 2; l >= 0; l--) {
+        const TailLevel &L = a.lv[l], &Cc = a.lv[l + 1];
+        const C9 A{L.op};
+        const int nz = L.op.nz, nx = L.op.nx, n = nz * nx, nzc = Cc.op.nz, nxc = Cc.op.nx;
+        const double *e = Cc.r;
+        for (int k = tid; k < nzc * nxc; k += T) {   // x += P e, thread per coarse block
+            const int Z = k / nxc, X = k % nxc;
+            const int i = 2 * Z * nx + 2 * X;
+            const bool xp = 2 * X + 1 < nx, zp = 2 * Z + 1 < nz, Xp = X + 1 < nxc, Zp = Z + 1 < nzc;
+            const double e00 = e[k];
+            const double e01 = Xp ? e[k + 1] : 0.0;
+            const double e10 = Zp ? e[k + nxc] : 0.0;
+            const double e11 = (Zp && Xp) ? e[k + nxc + 1] : 0.0;
+            L.x[i] += e00;
+            if (xp) L.x[i + 1] += L.w.hw[k] * e00 + L.w.he[k] * e01;
+            if (zp) L.x[i + nx] += L.w.vs[k] * e00 + L.w.vn[k] * e10;
+            if (zp && xp) L.x[i + nx + 1] += (L.w.csw[k] * e00 + L.w.cse[k] * e01) + (L.w.cnw[k] * e10 + L.w.cne[k] * e11);
+        }
+        __syncthreads();
+        for (int sweep = 0; sweep < a.nu; sweep++)
+            for (int col = 3; col >= 0; col--) {
+                tail_gs_colour(A, L.b, L.x, col >> 1, col & 1);
+                __syncthreads();
+            }
+        for (int i = tid; i < n; i += T) L.r[i] = L.x[i];
+        __syncthreads();
+    }
+}
+
 // x = S inv S b on the coarsest level (one CTA)
 __global__ void k_coarse_solve(const double *__restrict__ inv, const double *__restrict__ scale,
                                const double *__restrict__ b, double *__restrict__ x, int n, const PcgState *st)
@@ -695,6 +819,10 @@ void mg_vcycle(Solver &s, const double *r, double *ztmp, double *zout, PcgState 
     const Weights now{};
     std::function<void(size_t, bool)> cycle = [&](size_t l, bool zero_init) {
         Level &f = s.levels[l];
+        if ((int)l == s.tail_top) {   // this level and everything below it: one block, one launch
+            LAUNCH(k_tail_cycle, 1, kTailThreads, 0, s.stream, s.tail, zero_init ? 1 : 0, (const PcgState *)st);
+            return;
+        }
         if (l == nlev - 1) {   // coarsest: dense solve
             LAUNCH(k_coarse_solve, 1, 64, f.n * sizeof(double), s.stream, s.coarse_inv, s.coarse_scale,
                    (const double *)f.b, f.r, (int)f.n, st);

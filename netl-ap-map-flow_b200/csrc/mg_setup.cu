@@ -18,6 +18,8 @@
 // the coarse operators become indefinite (tools/proto_gth.py).
 #include "device_utils.cuh"
 
+#include <cstdlib>
+
 namespace lcl {
 
 // ------------------------------------------------------------------------------ edge weights
@@ -270,6 +272,25 @@ void mg_allocate(Solver &s)
     s.coarse_n = (int)s.levels.back().n;
     alloc_d(&s.coarse_inv, (size_t)s.coarse_n * s.coarse_n);
     alloc_d(&s.coarse_scale, s.coarse_n);
+    // the levels one block cycles in one launch (k_tail_cycle): the first coarse level with at most
+    // kTailCells cells and everything below it, if that is more than the dense level alone
+    s.tail_top = -1;
+    s.tail = TailArgs{};
+    if (s.levels[0].w.hw && !getenv("APM_LCL_NO_TAIL")) {
+        const size_t nlev = s.levels.size();
+        size_t top = 1;
+        while (top < nlev && s.levels[top].n > (size_t)kTailCells) top++;
+        if (top + 1 < nlev && nlev - top <= (size_t)kTailMaxLevels && s.coarse_n <= 64) {
+            s.tail_top = (int)top;
+            s.tail.nlev = (int)(nlev - top);
+            for (size_t l = top; l < nlev; l++) {
+                const Level &L = s.levels[l];
+                s.tail.lv[l - top] = TailLevel{L.view9(), L.w, L.x, L.b, L.r};
+            }
+            s.tail.inv = s.coarse_inv;
+            s.tail.scale = s.coarse_scale;
+        }
+    }
 }
 
 void mg_free(Solver &s)

@@ -231,21 +231,22 @@ __device__ __forceinline__ void down_norms_finalize(PcgState *st, int init, cons
 
 // Fine level, whole down leg in ONE launch: exact red/black sweep from a zero guess, the residual it
 // leaves (non-zero at red cells only) and its restriction to the coarse right-hand side.
-// A block stages b and the faces of a 26x58 tile plus frame -- 32 rows of 64 -- in shared memory with
+// A block stages b and the faces of a 42x58 tile plus frame -- 48 rows of 64 -- in shared memory with
 // asynchronous copies (everything in flight at once, zero-filled outside the grid, so the passes need
 // no neighbour logic and touch no global memory), then recomputes the frame instead of exchanging it:
 //   red  (rows -3..TZ+1)  x = b/diag                    -> needs nothing else
 //   black(rows -2..TZ)    x = (b + sum t x_red)/diag    -> exactly what the two-pass version computes
 //   residual at red cells (rows -1..TZ-1), in place over b
-//   coarse rhs of the 13x29 coarse points the tile owns = r(2Z,2X) + sum w r(2Z+-1,2X+-1)
+//   coarse rhs of the 21x29 coarse points the tile owns = r(2Z,2X) + sum w r(2Z+-1,2X+-1)
 // A warp walks rows, its lanes the cells of one colour in the row (32 per framed row): all index
 // arithmetic is shifts and adds, the row tests are warp-uniform.
 // Algorithmic traffic: b, tx, tz in, x out (32 B/cell) + 4 weights in, 1 rhs out per coarse point.
-constexpr int kDnTZ = 26, kDnTX = 58, kDnFL = 4, kDnFH = 2, kDnThreads = 512, kDnWarps = kDnThreads / 32;
+constexpr int kDnTZ = 42, kDnTX = 58, kDnFL = 4, kDnFH = 2, kDnThreads = 512, kDnWarps = kDnThreads / 32;
 constexpr int kDnH = kDnTZ + kDnFL + kDnFH, kDnW = kDnTX + kDnFL + kDnFH;
 constexpr size_t kDnSmem = 4 * (size_t)kDnH * kDnW * sizeof(double);
-static_assert(kDnW == 64 && kDnH == 2 * kDnWarps, "a framed row is two lane rounds, the framed tile two warp rounds");
-static_assert(kDnTZ / 2 <= kDnWarps && kDnTX / 2 <= 32, "one coarse point per thread");
+static_assert(kDnW == 64 && kDnH % kDnWarps == 0, "a framed row is two lane rounds, the framed tile whole warp rounds");
+static_assert(kDnTX / 2 <= 32, "a row of coarse points per warp");
+static_assert(2 * (kDnSmem + 2048) <= 228 * 1024, "two blocks per SM");
 
 // Shared-memory layout of a framed row: the 32 even columns first, then the 32 odd ones, so the lanes
 // of a warp walking one colour (stride 2 in x) touch consecutive doubles -- no bank conflicts -- and so
@@ -253,16 +254,16 @@ static_assert(kDnTZ / 2 <= kDnWarps && kDnTX / 2 <= 32, "one coarse point per th
 __device__ __forceinline__ int dn_pos(int row, int col) { return row * kDnW + (col >> 1) + ((col & 1) << 5); }
 
 // Stage b, the right face (tx; txl in column -1) and the upper face (tz; tzb in row -1) of every cell
-// of a framed 32x64 tile whose frame is F cells on the low sides, asynchronously and zero-filled
+// of a framed H x 64 tile whose frame is F cells on the low sides, asynchronously and zero-filled
 // outside the grid.  Lanes 0-15 take the even columns of a 32-column chunk, lanes 16-31 the odd ones:
 // one contiguous 256-byte read, two conflict-free 128-byte shared-memory writes.
-template <int F>
+template <int F, int H>
 __device__ __forceinline__ void stage_tile5(double *sb, double *stx, double *stz, const Fine5 &v,
                                             const double *__restrict__ b, int z0, int x0, int wy, int lane)
 {
     const int nz = v.nz, nx = v.nx;
 #pragma unroll
-    for (int row = wy; row < kDnH; row += kDnWarps) {
+    for (int row = wy; row < H; row += kDnWarps) {
         const int z = z0 + row - F;
         const bool zin = z >= 0 && z < nz, zface = z >= -1 && z < nz;
         const size_t zoff = zin ? (size_t)z * nx : 0;
@@ -295,18 +296,25 @@ k_down5(Fine5 v, Weights w, const double *__restrict__ b, double *__restrict__ x
     double acc[2] = {0.0, 0.0};
     for (long long t = blockIdx.x; t < (long long)tiles_x * tiles_z; t += gridDim.x) {
         const int z0 = (int)(t / tiles_x) * TZ, x0 = (int)(t % tiles_x) * TX;
-        stage_tile5<FL>(sb, stx, stz, v, b, z0, x0, wy, lane);
-        // restriction weights of this thread's coarse point ride along
-        const int Z = z0 / 2 + wy, X = x0 / 2 + lane;
-        const bool cin = wy < TZ / 2 && lane < TX / 2 && Z < nzc && X < nxc;
-        double wne = 0.0, wnw = 0.0, wse = 0.0, wsw = 0.0;
-        if (cin) {
-            const size_t bk = (size_t)Z * nxc + X;
-            const bool xm = X > 0, xp = 2 * X + 1 < nx, zm = Z > 0, zp = 2 * Z + 1 < nz;
-            if (zp && xp) wne = w.csw[bk];
-            if (zp && xm) wnw = w.cse[bk - 1];
-            if (zm && xp) wse = w.cnw[bk - nxc];
-            if (zm && xm) wsw = w.cne[bk - nxc - 1];
+        stage_tile5<FL, H>(sb, stx, stz, v, b, z0, x0, wy, lane);
+        // restriction weights of this thread's coarse points (rows wy, wy + 16 of the tile's 21 x 29) ride along
+        constexpr int CR = (TZ / 2 + kDnWarps - 1) / kDnWarps;
+        const int X = x0 / 2 + lane;
+        double wne[CR], wnw[CR], wse[CR], wsw[CR];
+        bool cin[CR];
+#pragma unroll
+        for (int c = 0; c < CR; c++) {
+            const int cr = wy + c * kDnWarps, Z = z0 / 2 + cr;
+            cin[c] = cr < TZ / 2 && lane < TX / 2 && Z < nzc && X < nxc;
+            wne[c] = wnw[c] = wse[c] = wsw[c] = 0.0;
+            if (cin[c]) {
+                const size_t bk = (size_t)Z * nxc + X;
+                const bool xm = X > 0, xp = 2 * X + 1 < nx, zm = Z > 0, zp = 2 * Z + 1 < nz;
+                if (zp && xp) wne[c] = w.csw[bk];
+                if (zp && xm) wnw[c] = w.cse[bk - 1];
+                if (zm && xp) wse[c] = w.cnw[bk - nxc];
+                if (zm && xm) wsw[c] = w.cne[bk - nxc - 1];
+            }
         }
         cp_async_wait_all();
         __syncthreads();
@@ -383,32 +391,38 @@ k_down5(Fine5 v, Weights w, const double *__restrict__ b, double *__restrict__ x
             }
         }
         __syncthreads();
-        if (cin) {
-            const int p = dn_pos(2 * wy + FL, 2 * lane + FL);  // even column: left neighbour p + 31, right p + 32
-            double s = sb[p];
-            s += wne * sb[p + W + 32];
-            s += wnw * sb[p + W + 31];
-            s += wse * sb[p - W + 32];
-            s += wsw * sb[p - W + 31];
-            bc[(size_t)Z * nxc + X] = s;
-        }
+#pragma unroll
+        for (int c = 0; c < CR; c++)
+            if (cin[c]) {
+                const int cr = wy + c * kDnWarps;
+                const int p = dn_pos(2 * cr + FL, 2 * lane + FL);  // even column: left neighbour p + 31, right p + 32
+                double s = sb[p];
+                s += wne[c] * sb[p + W + 32];
+                s += wnw[c] * sb[p + W + 31];
+                s += wse[c] * sb[p - W + 32];
+                s += wsw[c] * sb[p - W + 31];
+                bc[(size_t)(z0 / 2 + cr) * nxc + X] = s;
+            }
         __syncthreads();
     }
     grid_sum_finalize<2>(acc, partials, counter, [=](const double(&tot)[2]) { down_norms_finalize(st, init, tot); });
 }
 
 // Fine level, whole up leg in ONE launch, staged like k_down5: x += P e, one EXACT black/red sweep and
-// b.x (= r.z of PCG).  28x60 tiles with a 2-cell frame (32 rows of 64): the thread that owns a coarse
+// b.x (= r.z of PCG).  28x60 tiles with a 2-cell frame (32 rows of 64; taller tiles were measured
+// slower here: the x + P e operands are loaded synchronously, one round per 16 coarse rows): the thread that owns a coarse
 // 2x2 block builds x + P e for it while the asynchronous copies of b and the faces are in flight.
 constexpr int kUpTZ = 28, kUpTX = 60, kUpF = 2;
-static_assert(kUpTZ + 2 * kUpF == kDnH && kUpTX + 2 * kUpF == kDnW, "same framed tile as the down leg");
+constexpr int kUpH = kUpTZ + 2 * kUpF;
+constexpr size_t kUpSmem = 4 * (size_t)kUpH * kDnW * sizeof(double);
+static_assert(kUpH == 2 * kDnWarps && kUpTX + 2 * kUpF == kDnW, "one coarse block per thread; rows as wide as the down leg's");
 
 __global__ void __launch_bounds__(kDnThreads, 2)
 k_up5(Fine5 v, const double *__restrict__ b, const double *__restrict__ xin, double *__restrict__ xout, Weights w,
       const double *__restrict__ e, int nzc, int nxc, PcgState *st, int init, double *partials, unsigned int *counter)
 {
     if (stopped(st)) return;
-    constexpr int W = kDnW, H = kDnH, F = kUpF, TZ = kUpTZ, TX = kUpTX;
+    constexpr int W = kDnW, H = kUpH, F = kUpF, TZ = kUpTZ, TX = kUpTX;
     LCL_DYNAMIC_SMEM(double, smem);
     double *sb = smem, *stx = smem + H * W, *stz = smem + 2 * H * W, *sx = smem + 3 * H * W;
     const int nz = v.nz, nx = v.nx;
@@ -417,9 +431,11 @@ k_up5(Fine5 v, const double *__restrict__ b, const double *__restrict__ xin, dou
     double acc[2] = {0.0, 0.0};
     for (long long t = blockIdx.x; t < (long long)tiles_x * tiles_z; t += gridDim.x) {
         const int z0 = (int)(t / tiles_x) * TZ, x0 = (int)(t % tiles_x) * TX;
-        stage_tile5<F>(sb, stx, stz, v, b, z0, x0, wy, lane);
-        {   // x + P e of the coarse block (wy, lane) of the framed tile: rows 2wy, 2wy+1, columns 2lane, 2lane+1
-            const int bz = (z0 >> 1) - 1 + wy, bx = (x0 >> 1) - 1 + lane;
+        stage_tile5<F, H>(sb, stx, stz, v, b, z0, x0, wy, lane);
+#pragma unroll
+        for (int br = wy; br < H / 2; br += kDnWarps) {
+            // x + P e of the coarse block (br, lane) of the framed tile: rows 2br, 2br+1, columns 2lane, 2lane+1
+            const int bz = (z0 >> 1) - 1 + br, bx = (x0 >> 1) - 1 + lane;
             double v00 = 0.0, v01 = 0.0, v10 = 0.0, v11 = 0.0;
             if (bz >= 0 && bx >= 0 && bz < nzc && bx < nxc) {
                 const size_t bk = (size_t)bz * nxc + bx;
@@ -436,7 +452,7 @@ k_up5(Fine5 v, const double *__restrict__ b, const double *__restrict__ xin, dou
                 if (zp && xp)
                     v11 = xin[i + nx + 1] + ((w.csw[bk] * e00 + w.cse[bk] * e01) + (w.cnw[bk] * e10 + w.cne[bk] * e11));
             }
-            const int p = 2 * wy * W + lane;               // dn_pos(2 wy, 2 lane); the odd column sits 32 further
+            const int p = 2 * br * W + lane;               // dn_pos(2 br, 2 lane); the odd column sits 32 further
             sx[p] = v00;
             sx[p + 32] = v01;
             sx[p + W] = v10;
@@ -713,7 +729,7 @@ static int leg_grid(Solver &s, int tz, int tx)
 {
     if (!s.down_configured) {   // per device: the attribute lives in the context of the solver's GPU
         CUDA_CHECK(cudaFuncSetAttribute(k_down5, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDnSmem));
-        CUDA_CHECK(cudaFuncSetAttribute(k_up5, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDnSmem));
+        CUDA_CHECK(cudaFuncSetAttribute(k_up5, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kUpSmem));
         s.down_configured = true;
     }
     const long long tiles = (long long)div_up(s.nx, tx) * div_up(s.nz, tz);
@@ -738,7 +754,7 @@ double bench_launch_cycle(Solver &s, const std::string &name)
     };
     if (name == "up5" && s.levels.size() > 1 && s.levels[0].w.hw) {
         Level &c = s.levels[1];
-        LAUNCH(k_up5, up_grid(s), kDnThreads, kDnSmem, s.stream, v5, (const double *)s.r, (const double *)s.z, s.q,
+        LAUNCH(k_up5, up_grid(s), kDnThreads, kUpSmem, s.stream, v5, (const double *)s.r, (const double *)s.z, s.q,
                s.levels[0].w, (const double *)c.r, c.nz, c.nx, s.state, 0, part + 4 * kMaxPartials, cnt + 1);
         return 40.0 * n + (8.0 + 64.0) * (double)c.n;   // x, b, tx, tz in; x out; coarse e + 8 weights
     }
@@ -852,7 +868,7 @@ void mg_vcycle(Solver &s, const double *r, double *ztmp, double *zout, PcgState 
     if (1 >= s.w_lo && 1 <= s.w_hi && nlev > 2) cycle(1, false);
     {
         Level &c = s.levels[1];
-        LAUNCH(k_up5, up_grid(s), kDnThreads, kDnSmem, s.stream, v5, r, (const double *)ztmp, zout, s.levels[0].w,
+        LAUNCH(k_up5, up_grid(s), kDnThreads, kUpSmem, s.stream, v5, r, (const double *)ztmp, zout, s.levels[0].w,
                (const double *)c.r, c.nz, c.nx, st, init, part + 4 * kMaxPartials, cnt + 1);
     }
 }

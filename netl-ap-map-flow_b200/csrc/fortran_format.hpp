@@ -8,6 +8,7 @@
 // rounded conversion, which is also what libgfortran uses internally.
 #pragma once
 
+#include <charconv>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -99,6 +100,94 @@ inline std::string A(int w, const std::string &s)
 {
     if ((int)s.size() >= w) return s.substr(0, (size_t)w);
     return rjust(s, w);
+}
+
+// ---- the same edit descriptors for the bulk writers: std::to_chars (correctly rounded like printf,
+// several times faster) straight into the row buffer, no temporary strings.  tests/test_abi.py checks
+// them against F/E/G above on random and edge-case values.
+inline void append_padded(std::string &out, int w, const char *s, int n)
+{
+    if (n < w) out.append((size_t)(w - n), ' ');
+    out.append(s, (size_t)n);
+}
+
+inline void append_F(std::string &out, int w, int d, double x)
+{
+    if (std::isnan(x) || std::isinf(x)) { out += F(w, d, x); return; }
+    char buf[400];
+    auto r = std::to_chars(buf, buf + sizeof buf, x, std::chars_format::fixed, d);
+    if (r.ec != std::errc()) { out += F(w, d, x); return; }
+    char *s = buf;
+    int n = (int)(r.ptr - buf);
+    if (n > w) {   // gfortran drops the optional leading zero when the field is too narrow
+        if (n >= 2 && s[0] == '0' && s[1] == '.') { s++; n--; }
+        else if (n >= 3 && s[0] == '-' && s[1] == '0' && s[2] == '.') { s[1] = '-'; s++; n--; }
+    }
+    if (n > w) { out.append((size_t)(w > 0 ? w : 1), '*'); return; }
+    append_padded(out, w, s, n);
+}
+
+inline void append_E(std::string &out, int w, int d, double x)
+{
+    if (std::isnan(x) || std::isinf(x) || d > 40) { out += E(w, d, x); return; }
+    const bool neg = std::signbit(x);
+    const double a = std::fabs(x);
+    char buf[64], s[80];
+    int ex = 0, n = 0;
+    if (neg) s[n++] = '-';
+    s[n++] = '0';
+    s[n++] = '.';
+    if (a == 0.0) {
+        for (int k = 0; k < d; k++) s[n++] = '0';
+    } else {
+        auto r = std::to_chars(buf, buf + sizeof buf, a, std::chars_format::scientific, d - 1);   // D.DDDDe+XX
+        if (r.ec != std::errc()) { out += E(w, d, x); return; }
+        const char *e = buf;
+        while (*e != 'e') e++;
+        for (const char *p = buf; p < e; p++)
+            if (*p != '.') s[n++] = *p;
+        int v = 0;
+        for (const char *p = e + 2; p < r.ptr; p++) v = v * 10 + (*p - '0');
+        ex = (e[1] == '-' ? -v : v) + 1;
+    }
+    const int ax = ex < 0 ? -ex : ex;
+    if (ax < 100) {
+        s[n++] = 'E';
+        s[n++] = ex < 0 ? '-' : '+';
+        s[n++] = (char)('0' + ax / 10);
+        s[n++] = (char)('0' + ax % 10);
+    } else {
+        s[n++] = ex < 0 ? '-' : '+';
+        s[n++] = (char)('0' + ax / 100);
+        s[n++] = (char)('0' + ax / 10 % 10);
+        s[n++] = (char)('0' + ax % 10);
+    }
+    char *q = s;
+    if (n > w) {   // drop the leading zero: [-].ddddE+ee
+        if (neg) { s[1] = '-'; q = s + 1; }
+        else q = s + 1;
+        n--;
+    }
+    if (n > w) { out.append((size_t)(w > 0 ? w : 1), '*'); return; }
+    append_padded(out, w, q, n);
+}
+
+inline void append_G(std::string &out, int w, int d, double x)
+{
+    if (std::isnan(x) || std::isinf(x) || d > 40) { out += G(w, d, x); return; }
+    const double a = std::fabs(x);
+    if (a == 0.0) { append_F(out, w - 4, d - 1, x); out.append(4, ' '); return; }
+    char buf[64];
+    auto r = std::to_chars(buf, buf + sizeof buf, a, std::chars_format::scientific, d - 1);
+    if (r.ec != std::errc()) { out += G(w, d, x); return; }
+    const char *e = buf;
+    while (*e != 'e') e++;
+    int v = 0;
+    for (const char *p = e + 2; p < r.ptr; p++) v = v * 10 + (*p - '0');
+    const int s = (e[1] == '-' ? -v : v) + 1;
+    if (s < 0 || s > d) { append_E(out, w, d, x); return; }
+    append_F(out, w - 4, d - s, x);
+    out.append(4, ' ');
 }
 
 inline std::string rtrim(std::string s)

@@ -15,10 +15,12 @@
 #include <cerrno>
 #include <chrono>
 #include <cmath>
+#include <condition_variable>
 #include <cstdio>
 #include <cstring>
 #include <fstream>
 #include <functional>
+#include <mutex>
 #include <sstream>
 #include <string>
 #include <thread>
@@ -37,6 +39,8 @@ using ffmt::E;
 using ffmt::F;
 using ffmt::G;
 using ffmt::I;
+using ffmt::append_E;
+using ffmt::append_G;
 
 constexpr int kMaxFld = 100, kMaxLen = 256;   // STRING_MODULE.F:21-22
 
@@ -77,6 +81,19 @@ unsigned io_threads()
     return n > 32 ? 32 : n;
 }
 
+// APM_LCL_IO_TIMING=1: wall time of every stage of the file pipeline on stderr
+struct StageTimer {
+    bool on = getenv("APM_LCL_IO_TIMING") != nullptr;
+    std::chrono::steady_clock::time_point t = std::chrono::steady_clock::now();
+    void lap(const char *what)
+    {
+        if (!on) return;
+        const auto now = std::chrono::steady_clock::now();
+        fprintf(stderr, "[apm_lcl io] %-28s %8.1f ms\n", what, std::chrono::duration<double, std::milli>(now - t).count());
+        t = now;
+    }
+};
+
 template <class Fn>   // fn(row, std::string &out) appends the text of one row
 void write_rows_parallel(FILE *f, long long nrows, Fn fn)
 {
@@ -91,20 +108,51 @@ void write_rows_parallel(FILE *f, long long nrows, Fn fn)
         fwrite(buf.data(), 1, buf.size(), f);
         return;
     }
-    std::vector<std::string> bufs(T);
-    for (long long wave = 0; wave < nrows; wave += per_task * T) {
-        std::vector<std::thread> pool;
-        for (unsigned t = 0; t < T; t++) {
-            const long long b = wave + per_task * t, e = std::min(nrows, b + per_task);
-            if (b >= e) break;
-            pool.emplace_back([&, t, b, e]() {
-                bufs[t].clear();
-                for (long long r = b; r < e; r++) fn(r, bufs[t]);
-            });
+    // T formatting threads take chunks of per_task rows from a counter and fill a ring of buffers; this
+    // thread writes the chunks out in order while later ones are still being formatted.
+    const long long nchunks = (nrows + per_task - 1) / per_task;
+    const long long window = 2LL * T;
+    std::vector<std::string> bufs((size_t)window);
+    std::vector<long long> done((size_t)window, -1);   // chunk whose text the slot holds
+    std::mutex m;
+    std::condition_variable cv;
+    long long next = 0, written = 0;
+    std::vector<std::thread> pool;
+    for (unsigned t = 0; t < T; t++)
+        pool.emplace_back([&]() {
+            for (;;) {
+                long long ch;
+                {
+                    std::unique_lock<std::mutex> lock(m);
+                    ch = next++;
+                    if (ch >= nchunks) return;
+                    cv.wait(lock, [&]() { return ch < written + window; });   // its slot has been written out
+                }
+                std::string &buf = bufs[(size_t)(ch % window)];
+                buf.clear();
+                const long long b = ch * per_task, e = std::min(nrows, b + per_task);
+                for (long long r = b; r < e; r++) fn(r, buf);
+                {
+                    std::lock_guard<std::mutex> lock(m);
+                    done[(size_t)(ch % window)] = ch;
+                }
+                cv.notify_all();
+            }
+        });
+    for (long long ch = 0; ch < nchunks; ch++) {
+        {
+            std::unique_lock<std::mutex> lock(m);
+            cv.wait(lock, [&]() { return done[(size_t)(ch % window)] == ch; });
         }
-        for (auto &th : pool) th.join();
-        for (size_t t = 0; t < pool.size(); t++) fwrite(bufs[t].data(), 1, bufs[t].size(), f);
+        const std::string &buf = bufs[(size_t)(ch % window)];
+        fwrite(buf.data(), 1, buf.size(), f);
+        {
+            std::lock_guard<std::mutex> lock(m);
+            written = ch + 1;
+        }
+        cv.notify_all();
     }
+    for (auto &th : pool) th.join();
 }
 
 template <class Fn>   // fn(begin, end, slot) over [0, n) split into `slots` contiguous parts
@@ -800,7 +848,7 @@ void write_map_csv(FILE *f, const double *v, int nx, int nz, double scale)
     write_rows_parallel(f, nz, [=](long long z, std::string &line) {
         for (int x = 0; x < nx; x++) {
             if (x) line += ',';
-            line += G(15, 8, v[(size_t)z * nx + x] * scale);
+            append_G(line, 15, 8, v[(size_t)z * nx + x] * scale);
         }
         line += '\n';
     });
@@ -814,7 +862,7 @@ void write_vtk_scalars(Run &r, const char *name, const std::string &unit, const 
     const int nx = r.nx;
     write_rows_parallel(f, r.nz, [=](long long z, std::string &buf) {
         for (int x = 0; x < nx; x++) {
-            buf += E(14, 6, v[(size_t)z * nx + x] * scale);
+            append_E(buf, 14, 6, v[(size_t)z * nx + x] * scale);
             buf += x + 1 < nx ? " \n" : "\n";
         }
     });
@@ -878,7 +926,9 @@ int run(Run &r, int device)
     // READ_AP_MAP :411-591
     r.blank();
     r.message(" READING APERTURE MAP");
+    StageTimer timer;
     if (!read_data_map(r)) return 1;
+    timer.lap("read + parse map");
     const int nx = r.nx, nz = r.nz;
     const size_t n = (size_t)nx * nz;
     r.p.voxel_size = r.units.vox;
@@ -887,6 +937,7 @@ int run(Run &r, int device)
     if (r.percentile) {
         r.message("     CALCULATING APERTURE PERCENTILES OF MAP");
         perc_ap = percentiles(r.ap, r.perc);
+        timer.lap("aperture percentiles");
     }
     r.p.outlet_side = side_code(r.outlet_side);
 
@@ -902,6 +953,7 @@ int run(Run &r, int device)
         if (!(r.p.rel_tol > 0)) r.p.rel_tol = 1e-12;
         solve_rc = apm_lcl_solve(&r.p, r.ap.data(), nx, nz, device, &fo, &sc);
         if (solve_rc) solve_err = apm_lcl_last_error();
+        timer.lap("apm_lcl_solve (host buffers)");
     }
 
     r.message("     CONVERTING 2-D MAP ARRAY IN VOX TO VECTOR IN SI");
@@ -919,6 +971,7 @@ int run(Run &r, int device)
         for (size_t i = 0; i < n; i++) si_map[i] = clamped[i] * vox;
         double xc, zc;
         map_stats(si_map, nx, nz, r.aper_rms, r.aper_dev, xc, zc);
+        timer.lap("map_stats");
         r.x_corr = xc * r.p.avg_factor * vox;
         r.z_corr = zc * r.p.avg_factor * vox;
     }
@@ -1045,6 +1098,7 @@ int run(Run &r, int device)
         write_percentile_table(r, r.perc, percentiles(res, r.perc), "NORMALIZED RESIDUAL", "-");
     }
     r.blank();
+    timer.lap("scalars, log, percentiles");
     r.message(" WRITING DATA TO OUTPUT FILES...");
 
     // WRITE_STATS_FILE :1046-1209
@@ -1105,6 +1159,7 @@ int run(Run &r, int device)
         yl("AVERAGE TRANSMISSIBILTY", hom, "M^4"); yl("PRESSURE DIFFERENTIAL", dp, "PA"); yl("1-D EQUIV", nfq_o, u5);
         yl("PERC OF 1-D", flow_cf * 100, "-");
     }
+    timer.lap("stat files");
     write_map_csv(r.fmap, width.data(), nx, nz, r.dim_conv);
     r.message("     ADJUSTED APERTURE FILE COMPLETED");
     write_map_csv(r.fflox, qx.data(), nx, nz, r.rate_conv);
@@ -1113,6 +1168,7 @@ int run(Run &r, int device)
     r.message("     FLOW FILE COMPLETED");
     write_map_csv(r.fpres, pres.data(), nx, nz, r.pres_conv);
     r.message("     PRESSURE FILE COMPLETED");
+    timer.lap("5 csv maps");
 
     // WRITE_VTK_FILE :1215-1291
     {
@@ -1134,9 +1190,14 @@ int run(Run &r, int device)
                 // rows 0..nz-1 use the bottom corners of row iz, the last record the top corners of row nz-1
                 const int cz = iz < nz ? (int)iz - 1 : nz - 1;
                 const double Z = zs[(size_t)iz];
-                for (int ix = -1; ix < nx; ix++)
-                    buf += E(14, 6, xs[(size_t)(ix + 1)]) + " " + E(14, 6, sgn * (corner(clamped, nx, nz, cz, ix) * pm) / 2.0) +
-                           " " + E(14, 6, Z) + "\n";
+                for (int ix = -1; ix < nx; ix++) {
+                    append_E(buf, 14, 6, xs[(size_t)(ix + 1)]);
+                    buf += ' ';
+                    append_E(buf, 14, 6, sgn * (corner(clamped, nx, nz, cz, ix) * pm) / 2.0);
+                    buf += ' ';
+                    append_E(buf, 14, 6, Z);
+                    buf += '\n';
+                }
             });
         }
         r.message("         VTK POINTS OUTPUT TO FILE");
@@ -1154,12 +1215,16 @@ int run(Run &r, int device)
             write_rows_parallel(f, nz, [=](long long z, std::string &b2) {
                 for (int x = 0; x < nx; x++) {
                     const size_t i = (size_t)z * nx + x;
-                    b2 += E(14, 6, px[i] * rc) + " " + E(14, 6, 0.0) + " " + E(14, 6, pz[i] * rc) + "\n";
+                    append_E(b2, 14, 6, px[i] * rc);
+                    b2 += "   0.000000E+00 ";
+                    append_E(b2, 14, 6, pz[i] * rc);
+                    b2 += '\n';
                 }
             });
         }
         r.message("         VECTOR FLOW DATA OUTPUT TO VTK FILE");
     }
+    timer.lap("vtk file");
     r.blank();
     r.message(" DEALLOCATED ALL ARRAYS");
     r.blank();

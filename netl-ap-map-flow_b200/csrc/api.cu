@@ -47,6 +47,7 @@ static void solver_free(Solver *s)
 #ifndef LCL_CPU_SIM
     if (s->iter_graph) cudaGraphExecDestroy(s->iter_graph);
 #endif
+    if (s->copy_stream) cudaStreamDestroy(s->copy_stream);
     if (s->stream) cudaStreamDestroy(s->stream);
     delete s;
 }
@@ -68,6 +69,7 @@ static Solver *solver_new(int device, int nx, int nz)
         CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
         s->num_sms = prop.multiProcessorCount;
         CUDA_CHECK(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+        CUDA_CHECK(cudaStreamCreateWithFlags(&s->copy_stream, cudaStreamNonBlocking));
         double **fields[] = {&s->ap, &s->width, &s->tx, &s->tz, &s->x, &s->r, &s->d, &s->q, &s->z};
         for (auto f : fields) alloc_d(f, s->n);
         alloc_d(&s->txl, nz);
@@ -196,6 +198,19 @@ static void do_solve(Solver &s, const apm_lcl_params &p, const double *aperture,
     const double *ap_dev = stage_aperture(s, aperture);
     CUDA_CHECK(cudaEventRecord(s.ev[0], s.stream));
     launch_conductance(s, p, ap_dev);
+    // WIDTH is final here: a host caller gets it over a second stream while the solve runs (PCIe is idle
+    // until the other fields exist); the guard makes sure the copy has landed on every way out
+    struct CopyGuard {
+        cudaStream_t st;
+        bool active = false;
+        ~CopyGuard() { if (active) cudaStreamSynchronize(st); }
+    } early{s.copy_stream};
+    if (out && out->aperture && !is_device_ptr(out->aperture)) {
+        CUDA_CHECK(cudaEventRecord(s.ev[5], s.stream));
+        CUDA_CHECK(cudaStreamWaitEvent(s.copy_stream, s.ev[5], 0));
+        CUDA_CHECK(cudaMemcpyAsync(out->aperture, s.width, s.n * sizeof(double), cudaMemcpyDeviceToHost, s.copy_stream));
+        early.active = true;
+    }
     mg_setup(s);
     CUDA_CHECK(cudaEventRecord(s.ev[1], s.stream));
 
@@ -250,7 +265,7 @@ static void do_solve(Solver &s, const apm_lcl_params &p, const double *aperture,
     CUDA_CHECK(cudaEventRecord(s.ev[3], s.stream));
     for (int k = 0; k < 5; k++) copy_out(s, user[k], *slot[k], s.n);
     copy_out(s, out->pressure, s.x, s.n);
-    copy_out(s, out->aperture, s.width, s.n);
+    if (!early.active) copy_out(s, out->aperture, s.width, s.n);
     CUDA_CHECK(cudaEventRecord(s.ev[4], s.stream));
     read_map_scalars(s, p, sc);   // synchronises the stream
 

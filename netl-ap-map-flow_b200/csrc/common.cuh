@@ -137,6 +137,7 @@ struct Solver {
     int device = 0, nx = 0, nz = 0;
     size_t n = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t copy_stream = nullptr;   // device -> host copies that can run beside the solve
     int num_sms = 148;
     // fine level
     double *ap = nullptr, *width = nullptr, *tx = nullptr, *tz = nullptr, *txl = nullptr, *tzb = nullptr;

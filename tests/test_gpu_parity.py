@@ -115,6 +115,17 @@ def test_synthetic_lognormal_maps_vs_oracle(n, contact):
         assert so["zeros"] > 0.15 * n * n
 
 
+@pytest.mark.parametrize("shape", [(131, 257), (173, 119), (59, 175), (86, 61)])
+@pytest.mark.parametrize("side", [LEFT, RIGHT, TOP, BOTTOM])
+def test_ragged_multi_tile_maps_all_sides_vs_oracle(shape, side):
+    """Shapes that are no multiple of any kernel's tile (42x58 / 28x60 fine legs, 16x64 coarse tiles), odd
+    and even widths (the paired double2 stores need an even nx), every outlet side, with contact cells."""
+    nz, nx = shape
+    a = synth_aperture(nz, nx, seed=nz + nx, sigma_c=4, contact=0.15, sigma_k=6)
+    vertical = side in (TOP, BOTTOM)
+    check_against_oracle(synth_params(outlet_side=side), a, pmask=anchored_open_mask(a, 1e-4, vertical))
+
+
 def test_invalid_inputs_fail_with_reference_messages():
     a = synth_aperture(8, 8, seed=1, sigma_c=0)
     with pytest.raises(lcl._lib.LclError, match="INVALID BOUNDARY"):

@@ -22,6 +22,15 @@
 
 namespace lcl {
 
+// Galerkin coarsening next to contact regions produces a few rows that are no M-matrix rows (negative
+// couplings = positive off-diagonals).  Taken at face value they give interpolation weights outside
+// [0,1], row sums of -8, or a non-positive denominator (then the point got no interpolation at all: a
+// hole in P, one slow mode each).  As in classical AMG only the positive couplings interpolate; the
+// negative ones are left out of numerator and denominator alike, so weights stay in [0,1] and sum to
+// 1 - deficit.  On M-matrix rows (the whole fine level) nothing changes.
+__device__ __forceinline__ double pos(double g) { return g > 0.0 ? g : 0.0; }
+__device__ __forceinline__ double neg(double g) { return g < 0.0 ? g : 0.0; }
+
 // ------------------------------------------------------------------------------ edge weights
 template <class Op>
 __global__ void __launch_bounds__(kBlock)
@@ -38,9 +47,9 @@ k_weights_edges(Op A, int nzc, int nxc, Weights w)
         {   // h-edge point (2Z, 2X+1)
             const int z = 2 * Z, x = 2 * X + 1;
             if (x < nx) {
-                const double west = A.g(z, x, 0, -1) + A.g(z, x, -1, -1) + A.g(z, x, 1, -1);
-                const double east = (x + 1 < nx) ? A.g(z, x, 0, 1) + A.g(z, x, -1, 1) + A.g(z, x, 1, 1) : 0.0;
-                const double sp = A.S(z, x);
+                const double west = pos(A.g(z, x, 0, -1)) + pos(A.g(z, x, -1, -1)) + pos(A.g(z, x, 1, -1));
+                const double east = (x + 1 < nx) ? pos(A.g(z, x, 0, 1)) + pos(A.g(z, x, -1, 1)) + pos(A.g(z, x, 1, 1)) : 0.0;
+                const double sp = pos(A.S(z, x));
                 const double den = (west + east) + sp;
                 if (den > 0.0) { hw = west / den; he = east / den; th = sp / den; }
                 else th = 1.0;
@@ -49,9 +58,9 @@ k_weights_edges(Op A, int nzc, int nxc, Weights w)
         {   // v-edge point (2Z+1, 2X)
             const int z = 2 * Z + 1, x = 2 * X;
             if (z < nz) {
-                const double south = A.g(z, x, -1, 0) + A.g(z, x, -1, -1) + A.g(z, x, -1, 1);
-                const double north = (z + 1 < nz) ? A.g(z, x, 1, 0) + A.g(z, x, 1, -1) + A.g(z, x, 1, 1) : 0.0;
-                const double sp = A.S(z, x);
+                const double south = pos(A.g(z, x, -1, 0)) + pos(A.g(z, x, -1, -1)) + pos(A.g(z, x, -1, 1));
+                const double north = (z + 1 < nz) ? pos(A.g(z, x, 1, 0)) + pos(A.g(z, x, 1, -1)) + pos(A.g(z, x, 1, 1)) : 0.0;
+                const double sp = pos(A.S(z, x));
                 const double den = (south + north) + sp;
                 if (den > 0.0) { vs = south / den; vn = north / den; tv = sp / den; }
                 else tv = 1.0;
@@ -77,14 +86,21 @@ k_weights_centres(Op A, int nzc, int nxc, Weights w)
         double tc = 0.0;
         const int z = 2 * Z + 1, x = 2 * X + 1;
         if (z < nz && x < nx) {
-            const double dg = A.diag(z, x);
+            // diagonal with the negative couplings taken out again: S + (sum of the positive couplings)
+            double dg = A.diag(z, x);
+#pragma unroll
+            for (int dz = -1; dz <= 1; dz++)
+#pragma unroll
+                for (int dx = -1; dx <= 1; dx++)
+                    if (dz != 0 || dx != 0) dg -= neg(A.g(z, x, dz, dx));
+            dg -= neg(A.S(z, x));
             if (dg > 0.0) {
                 // deficit: own absorption + what the four edge neighbours already lack
-                double def = A.S(z, x);
-                def += A.g(z, x, -1, 0) * w.th[(size_t)Z * nxc + X];
-                if (z + 1 < nz) def += A.g(z, x, 1, 0) * w.th[(size_t)(Z + 1) * nxc + X];
-                def += A.g(z, x, 0, -1) * w.tv[(size_t)Z * nxc + X];
-                if (x + 1 < nx) def += A.g(z, x, 0, 1) * w.tv[(size_t)Z * nxc + X + 1];
+                double def = pos(A.S(z, x));
+                def += pos(A.g(z, x, -1, 0)) * w.th[(size_t)Z * nxc + X];
+                if (z + 1 < nz) def += pos(A.g(z, x, 1, 0)) * w.th[(size_t)(Z + 1) * nxc + X];
+                def += pos(A.g(z, x, 0, -1)) * w.tv[(size_t)Z * nxc + X];
+                if (x + 1 < nx) def += pos(A.g(z, x, 0, 1)) * w.tv[(size_t)Z * nxc + X + 1];
                 tc = def / dg;
 #pragma unroll
                 for (int k = 0; k < 4; k++) {
@@ -94,14 +110,14 @@ k_weights_centres(Op A, int nzc, int nxc, Weights w)
                         // to the deficit only through the edge neighbours' own (zero) weights
                         continue;
                     }
-                    double acc = A.g(z, x, cz, cx);
+                    double acc = pos(A.g(z, x, cz, cx));
                     {   // via the h-edge point (z+cz, x): block row (cz<0 ? Z : Z+1), block col X
                         const size_t hb = (size_t)(cz < 0 ? Z : Z + 1) * nxc + X;
-                        acc += A.g(z, x, cz, 0) * (cx < 0 ? w.hw[hb] : w.he[hb]);
+                        acc += pos(A.g(z, x, cz, 0)) * (cx < 0 ? w.hw[hb] : w.he[hb]);
                     }
                     {   // via the v-edge point (z, x+cx): block row Z, block col (cx<0 ? X : X+1)
                         const size_t vb = (size_t)Z * nxc + (cx < 0 ? X : X + 1);
-                        acc += A.g(z, x, 0, cx) * (cz < 0 ? w.vs[vb] : w.vn[vb]);
+                        acc += pos(A.g(z, x, 0, cx)) * (cz < 0 ? w.vs[vb] : w.vn[vb]);
                     }
                     c[k] = acc / dg;
                 }

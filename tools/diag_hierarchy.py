@@ -225,3 +225,25 @@ if __name__ == "__main__":
     sc_ = np.abs(np.sqrt(d3) * e.reshape(nz3, nx3)).max()
     for zz in zs:
         print("%4d " % zz + " ".join("%7.3f" % (Ae[zz, xx] / sc_) for xx in xs))
+    if os.environ.get("DIAG_STAGES"):
+        print("---- the slow mode through one two-level cycle, D^1/2 scaled, window around the peak")
+        sq = np.sqrt(H.diag[Ld])
+        def show(tag, v):
+            vv = (sq * v).reshape(nz3, nx3) / sc_
+            print(tag)
+            for zz in zs:
+                print("%4d " % zz + " ".join("%7.3f" % vv[zz, xx] for xx in xs))
+        x = e.copy(); bb = np.zeros_like(e)
+        show("start", x)
+        H.smooth(Ld, x, bb, True, nu); show("after pre-smoothing", x)
+        r = bb - A3 @ x
+        ec = lu4.solve(P3.T @ r)
+        corr = P3 @ ec
+        show("coarse correction P e_c (to be added)", corr)
+        x += corr; show("after coarse correction", x)
+        H.smooth(Ld, x, bb, False, nu); show("after post-smoothing", x)
+        nzc, nxc = H.shape[Ld + 1]
+        print("coarse-level log10 diag around (window/2):")
+        d4 = H.diag[Ld + 1].reshape(nzc, nxc)
+        for zz in range(zs[0] // 2, zs[-1] // 2 + 1):
+            print("%4d " % zz + " ".join("%7.1f" % np.log10(d4[zz, xx]) for xx in range(xs[0] // 2, xs[-1] // 2 + 1)))

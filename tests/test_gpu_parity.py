@@ -156,12 +156,14 @@ def test_full_size_properties_2048(n, contact):
     main = anchored_open_mask(a)
     assert np.abs(f["pressure"] - g["pressure"])[main].max() / 1000.0 < 1e-6
     assert np.abs(f["flow_z"] - g["flow_z"]).max() <= 1e-6 * np.abs(g["flow_z"]).max()
-    assert f["pressure"].min() >= -1e-6 and f["pressure"].max() <= 1000.0 + 1e-6
+    # discrete maximum principle where f64 determines the pressure (floating pockets and the contact cells
+    # slaved to them are left where the early iterates put them, DESIGN.md "Floating pockets")
+    assert f["pressure"][main].min() >= -1e-6 and f["pressure"][main].max() <= 1000.0 + 1e-6
     _, _, trz, _ = lcl.conductance(synth_params(), a)
     q_in, q_out = _inflow_outflow(f, 1000.0, 0.0, trz)
     assert q_in == pytest.approx(q_out, rel=1e-7)
     assert abs(s["flow"]) == pytest.approx(q_out, rel=1e-6)
-    assert s["iterations"] < (20 if contact == 0.0 else 40)   # 11 and 27 measured: a weaker cycle shows here first
+    assert s["iterations"] < 25   # 11 and 17 measured: a weaker cycle shows here first
 
 
 def test_torch_cuda_tensor_io_matches_host_io():

@@ -6,7 +6,7 @@
 //                                                                          in registers, never stored)
 //   COEF                       apmapflow/src/APM_MODULE.F:142-271         (tapered-plate half cells)
 //   FLOW_BOUNDARY              apmapflow/src/APM_MODULE.F:277-376         (2x / 0 boundary faces)
-// Roofline: 8 B read + 24 B written per cell, but ~4 atan + 4 tan in FP64 per cell make it
+// Roofline: 8 B read + 24 B written per cell, but 4 atan and a dozen divisions in FP64 per cell make it
 // FP64-pipe bound, not HBM bound.  It runs once per solve.
 #include "device_utils.cuh"
 
@@ -26,11 +26,15 @@ __device__ __forceinline__ double clampa(double a, double high, double low)
 
 // One half-cell Stokes tapered-plate term (APM_MODULE.F:200-205).  a,b in the order the source
 // multiplies them; INT(1E9*x)==0 restated as |1e9 x| < 1 (no trap on overflow).
+// tan(theta) is the argument of the atan again: the reference evaluates TAN(ATAN(u)), which is u up to
+// the last ulp or two of the two libm calls -- the same uncertainty any other libm has, and what the
+// 1e-9 parity bar on conductances already allows for -- so the tangent (half of this kernel's FP64
+// work) is not recomputed.
 __device__ __forceinline__ double tapered_b3(double a, double b, double dhalf)
 {
-    const double theta = atan(fabs(a - b) / dhalf);
+    const double t = fabs(a - b) / dhalf;
+    const double theta = atan(t);
     const double w3 = ((2.0 * (a * a)) * (b * b)) / (a + b);
-    const double t = tan(theta);
     const double x = t - theta;
     if (fabs(1e9 * x) < 1.0) return w3;
     return ((w3 * 3.0) * x) / ((t * t) * t);

@@ -121,6 +121,34 @@ __device__ __forceinline__ double pdeficit(const Weights &w, int nxc, int qz, in
     return (qx & 1) ? w.th[b] : 0.0;
 }
 
+// The same two lookups with the fine point given RELATIVE to the coarse point (Z,X) that a thread owns:
+// fine point (2Z + fz, 2X + fx), coarse point (Z + jz, X + jx).  In fully unrolled loops all four
+// offsets are compile-time constants, so the geometry tests fold away and only the loads of the
+// structurally non-zero weights remain (the Galerkin kernel went from 3.9 to ... ms with this).
+__device__ __forceinline__ double pweight_rel(const Weights &w, int nzc, int nxc, int Z, int X, int fz, int fx, int jz,
+                                              int jx)
+{
+    const int dz = fz - 2 * jz, dx = fx - 2 * jx;
+    if (dz < -1 || dz > 1 || dx < -1 || dx > 1) return 0.0;
+    const int Jz = Z + jz, Jx = X + jx;
+    if (Jz < 0 || Jx < 0 || Jz >= nzc || Jx >= nxc) return 0.0;
+    if (dz == 0 && dx == 0) return 1.0;
+    // block that owns the fine point: floor(fz / 2), floor(fx / 2) blocks away from (Z, X)
+    const int boz = fz >= 0 ? fz / 2 : -((1 - fz) / 2), box = fx >= 0 ? fx / 2 : -((1 - fx) / 2);
+    const size_t b = (size_t)(Z + boz) * nxc + (X + box);
+    if (dz == 0) return dx == 1 ? w.hw[b] : w.he[b];
+    if (dx == 0) return dz == 1 ? w.vs[b] : w.vn[b];
+    if (dz == 1) return dx == 1 ? w.csw[b] : w.cse[b];
+    return dx == 1 ? w.cnw[b] : w.cne[b];
+}
+__device__ __forceinline__ double pdeficit_rel(const Weights &w, int nxc, int Z, int X, int fz, int fx)
+{
+    const int boz = fz >= 0 ? fz / 2 : -((1 - fz) / 2), box = fx >= 0 ? fx / 2 : -((1 - fx) / 2);
+    const size_t b = (size_t)(Z + boz) * nxc + (X + box);
+    if (fz & 1) return (fx & 1) ? w.tc[b] : w.tv[b];
+    return (fx & 1) ? w.th[b] : 0.0;
+}
+
 // ---------------------------------------------------------------------------------------------
 // Deterministic grid reduction with an in-kernel finalizer ("last block done").  Every block
 // contributes NV partial sums; the block that arrives last adds them up in a fixed order and runs

@@ -146,15 +146,20 @@ k_galerkin(Op A, int nzc, int nxc, Weights w, double *__restrict__ Sc, double *_
         if (Z >= nzc || X >= nxc) continue;
         double acc[4] = {0.0, 0.0, 0.0, 0.0};
         double sabs = 0.0;
-        const int Jz[4] = {Z, Z + 1, Z + 1, Z + 1};
-        const int Jx[4] = {X + 1, X, X + 1, X - 1};
-        for (int pz = 2 * Z - 1; pz <= 2 * Z + 1; pz++) {
+        constexpr int jz[4] = {0, 1, 1, 1}, jx[4] = {1, 0, 1, -1};   // E, N, NE, NW of (Z, X)
+        // every loop runs over offsets relative to (2Z, 2X) and is fully unrolled, so which weights exist
+        // for which (p, q, J) is decided at compile time
+#pragma unroll
+        for (int a = -1; a <= 1; a++) {
+            const int pz = 2 * Z + a;
             if (pz < 0 || pz >= nz) continue;
-            for (int px = 2 * X - 1; px <= 2 * X + 1; px++) {
+#pragma unroll
+            for (int bb = -1; bb <= 1; bb++) {
+                const int px = 2 * X + bb;
                 if (px < 0 || px >= nx) continue;
-                const double wI = pweight(w, nzc, nxc, pz, px, Z, X);
+                const double wI = pweight_rel(w, nzc, nxc, Z, X, a, bb, 0, 0);
                 if (wI == 0.0) continue;
-                const double tp = pdeficit(w, nxc, pz, px);
+                const double tp = pdeficit_rel(w, nxc, Z, X, a, bb);
                 double as = A.S(pz, px) * (1.0 - tp);
 #pragma unroll
                 for (int dz = -1; dz <= 1; dz++) {
@@ -166,12 +171,13 @@ k_galerkin(Op A, int nzc, int nxc, Weights w, double *__restrict__ Sc, double *_
                         if (qx < 0 || qx >= nx) continue;
                         const bool self = (dz == 0 && dx == 0);
                         const double gpq = self ? 0.0 : A.g(pz, px, dz, dx);
-                        const double a = self ? A.diag(pz, px) : -gpq;
-                        if (a == 0.0) continue;
-                        if (!self) as += gpq * (pdeficit(w, nxc, qz, qx) - tp);
-                        const double wa = wI * a;
+                        const double av = self ? A.diag(pz, px) : -gpq;
+                        if (av == 0.0) continue;
+                        if (!self) as += gpq * (pdeficit_rel(w, nxc, Z, X, a + dz, bb + dx) - tp);
+                        const double wa = wI * av;
 #pragma unroll
-                        for (int j = 0; j < 4; j++) acc[j] += wa * pweight(w, nzc, nxc, qz, qx, Jz[j], Jx[j]);
+                        for (int j = 0; j < 4; j++)
+                            acc[j] += wa * pweight_rel(w, nzc, nxc, Z, X, a + dz, bb + dx, jz[j], jx[j]);
                     }
                 }
                 sabs += wI * as;

@@ -86,9 +86,16 @@ static Solver *solver_new(int device, int nx, int nz)
         if (const char *e = getenv("APM_LCL_NU_L1")) s->nu_coarse = atoi(e);     // tuning knobs
         if (const char *e = getenv("APM_LCL_NU_DEEP")) s->nu_deep = atoi(e);
         s->tail.nu = s->tail_top == 1 ? s->nu_coarse : s->nu_deep;
-        // large maps: levels 3 and 4 are visited twice per cycle (measured: 8192^2 without contact 108 -> 76 ms,
-        // 4096^2 with contact 55 -> 50 ms; below 4096^2 the extra launches cost more than they save)
-        if (s->n >= ((size_t)1 << 24)) { s->w_lo = 3; s->w_hi = 4; }
+        // large maps: the mid levels from 3 down to the last one with at least 512^2 cells (but at least
+        // level 4) are visited twice per cycle.  Measured with 20 % contact: 8192^2 V-cycle 95 ms, levels 3-4
+        // 71 ms, 3-5 76 ms; 16384^2 levels 3-4 389 ms, 3-5 312 ms; below 4096^2 the extra launches cost
+        // more than they save
+        if (s->n >= ((size_t)1 << 24)) {
+            s->w_lo = 3;
+            s->w_hi = 4;
+            for (size_t l = 5; l < s->levels.size(); l++)
+                if (s->levels[l].n >= ((size_t)1 << 18)) s->w_hi = (int)l;
+        }
         if (const char *e = getenv("APM_LCL_W_LO")) s->w_lo = atoi(e);
         if (const char *e = getenv("APM_LCL_W_HI")) s->w_hi = atoi(e);
     } catch (...) {

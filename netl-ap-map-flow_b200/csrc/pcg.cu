@@ -180,7 +180,8 @@ int pcg_solve(Solver &s, const BoundaryValues &bv, double rel_tol, int max_iter,
     {   // pointwise stagnation test: no pressure moved by more than 2.5e-7 of the pressure scale in the
         // last two updates (global residual norms do not see hydraulically isolated islands)
         const double ps = fmax(fmax(fabs(bv.left), fabs(bv.right)), fmax(fabs(bv.bottom), fabs(bv.top)));
-        h.dx_tol = 2.5e-7 * (ps > 0 ? ps : 1.0);
+        const char *knob = getenv("APM_LCL_DX_TOL");   // relative; 2.5e-7 keeps weakly connected cells within the 1e-6 parity bar
+        h.dx_tol = (knob ? atof(knob) : 2.5e-7) * (ps > 0 ? ps : 1.0);
         h.dx = h.dx_prev = h.dx_prev2 = 1e300;
     }
     const bool debug = getenv("APM_LCL_DEBUG") != nullptr;

@@ -34,11 +34,16 @@ __device__ __forceinline__ double tapered_b3(double a, double b, double dhalf)
 {
     const double t = fabs(a - b) / dhalf;
     const double theta = atan(t);
-    const double w3 = ((2.0 * (a * a)) * (b * b)) / (a + b);
     const double x = t - theta;
-    if (fabs(1e9 * x) < 1.0) return w3;
-    return ((w3 * 3.0) * x) / ((t * t) * t);
+    const double num = (2.0 * (a * a)) * (b * b);
+    if (fabs(1e9 * x) < 1.0) return num / (a + b);
+    // W3 * 3 x / t^3 with W3 = num / (a + b): one division instead of two (FP64 divisions are what this
+    // kernel spends its time on; the result moves by an ulp, the parity bar on conductances is 1e-9)
+    return ((num * 3.0) * x) / ((a + b) * ((t * t) * t));
 }
+
+// two half-cell terms in series across a face: 1 / (d/B1 + d/B2) = B1 B2 / (d (B1 + B2)), one division
+__device__ __forceinline__ double series(double b1, double b2, double d) { return (b1 * b2) / (d * (b1 + b2)); }
 
 struct ApView {
     const double *a;
@@ -111,7 +116,7 @@ k_conductance(const double *__restrict__ ap, int nz, int nx, CondParams p, doubl
             if (x < nx - 1) {
                 const double wn = width_of(A.at(z, x + 1), p);
                 const double bf3 = tapered_b3(rht, wn, dbp);
-                fx = (1.0 / (dbp / bp3 + dbp / bf3)) * (p.dz / 12) / p.visc;   // :213,266
+                fx = series(bp3, bf3, dbp) * (p.dz / 12) / p.visc;           // :213,266
                 if (x == 0) txl[z] = lr_outlet ? 2 * fx : 0.0;                 // :309,324 / :339,354
             } else {
                 fx = (p.dz * bp3) / (12.0 * p.dx) / p.visc;                    // :249
@@ -128,7 +133,7 @@ k_conductance(const double *__restrict__ ap, int nz, int nx, CondParams p, doubl
             if (z < nz - 1) {
                 const double wn = width_of(A.at(z + 1, x), p);
                 const double bf3 = tapered_b3(top, wn, dbp);
-                fz = (1.0 / (dbp / bp3 + dbp / bf3)) * (p.dx / 12) / p.visc;   // :235
+                fz = series(bp3, bf3, dbp) * (p.dx / 12) / p.visc;           // :235
                 if (z == 0) tzb[x] = lr_outlet ? 0.0 : 2 * fz;                 // :311 / :341
             } else {
                 fz = (p.dz * bp3) / (12.0 * p.dx) / p.visc;                    // :262 (sic DZ/DX)

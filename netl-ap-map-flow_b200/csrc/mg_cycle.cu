@@ -221,9 +221,12 @@ __device__ __forceinline__ void down_norms_finalize(PcgState *st, int init, cons
         // Residual norms are met.  Keep iterating only while every update still shrinks the
         // largest pointwise pressure change: that is how weakly connected cells (which global
         // norms do not see) reach 1e-6.  If the change grows twice in a row (or after 12 such
-        // extra iterations) what is left are floating pockets, so stop.
+        // extra iterations) what is left are floating pockets, so stop.  A change of more than
+        // 2.5e-3 of the pressure scale while both norms are at rel_tol is a pocket too: its residual is
+        // rounding noise, divided by a leak conductance 1e-14 of everything else.
         st->res_ok += 1;
-        if ((st->dx <= st->dx_tol && st->dx_prev <= st->dx_tol) || (st->dx > st->dx_prev && st->dx_prev > st->dx_prev2) || st->res_ok > 12)
+        if ((st->dx <= st->dx_tol && st->dx_prev <= st->dx_tol) || (st->dx > st->dx_prev && st->dx_prev > st->dx_prev2) ||
+            st->dx > 1e4 * st->dx_tol || st->res_ok > 12)
             st->converged = 1;
     }
     if (!(tot[0] == tot[0]) || !(tot[1] == tot[1])) st->failed = 1;
@@ -717,7 +720,8 @@ k_dot_norms(const double *__restrict__ b, const double *__restrict__ x, Fine5 v,
         st->rz = tot[2];
         if (!init && tot[0] <= st->tol2 * st->bb && tot[1] <= st->tol2 * st->bs) {
             st->res_ok += 1;
-            if ((st->dx <= st->dx_tol && st->dx_prev <= st->dx_tol) || (st->dx > st->dx_prev && st->dx_prev > st->dx_prev2) || st->res_ok > 12)
+            if ((st->dx <= st->dx_tol && st->dx_prev <= st->dx_tol) || (st->dx > st->dx_prev && st->dx_prev > st->dx_prev2) ||
+            st->dx > 1e4 * st->dx_tol || st->res_ok > 12)
                 st->converged = 1;
         }
     });

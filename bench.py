@@ -69,47 +69,79 @@ def synth_map_torch(n, seed, device, contact=0.2, sigma_c=8.0, sigma_k=16.0):
 
 
 class ClockSampler(object):
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    """SM clock and clock-event (throttle) reasons sampled DURING the timed region (B200_PROFILING.md's
+    clocks line).  NVML is polled in-process every 10 ms -- a timed region of a few solves lasts a few
+    hundred ms, less than it takes an nvidia-smi process to start; nvidia-smi -lms is the fallback."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
+    NAMES = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
 
     def __init__(self, index):
-        self.rows, self.proc, self.index = [], None, index
+        self.rows, self.proc, self.index = [], None, index   # rows: (sm MHz, max MHz, set of reasons)
+        self.nvml, self.handle, self.thread, self.stop_flag = None, None, None, threading.Event()
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            dev = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+            ids = [d for d in dev.split(",") if d.strip()]
+            phys = int(ids[index]) if ids and all(d.strip().isdigit() for d in ids) and index < len(ids) else index
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            pynvml.nvmlDeviceGetClockInfo(self.handle, pynvml.NVML_CLOCK_SM)
+            self.nvml = pynvml
+        except Exception:
+            self.nvml = None
+
+    def _poll_nvml(self):
+        n, h = self.nvml, self.handle
+        bits = ((n.nvmlClocksThrottleReasonHwSlowdown, "hw_slowdown"),
+                (n.nvmlClocksThrottleReasonHwThermalSlowdown, "hw_thermal_slowdown"),
+                (n.nvmlClocksThrottleReasonSwThermalSlowdown, "sw_thermal_slowdown"),
+                (n.nvmlClocksThrottleReasonSwPowerCap, "sw_power_cap"))
+        mx = float(n.nvmlDeviceGetMaxClockInfo(h, n.NVML_CLOCK_SM))
+        while not self.stop_flag.is_set():
+            try:
+                sm = float(n.nvmlDeviceGetClockInfo(h, n.NVML_CLOCK_SM))
+                mask = int(n.nvmlDeviceGetCurrentClocksThrottleReasons(h))
+                self.rows.append((sm, mx, {name for bit, name in bits if mask & bit}))
+            except Exception:
+                pass
+            self.stop_flag.wait(0.01)
+
+    def _read_smi(self):
+        for line in self.proc.stdout:
+            r = [c.strip() for c in line.split(",")]
+            try:
+                self.rows.append((float(r[0]), float(r[1]),
+                                  {name for name, v in zip(self.NAMES, r[3:7]) if v.lower().startswith("active")}))
+            except (ValueError, IndexError):
+                continue
 
     def start(self):
+        if self.nvml:
+            self.thread = threading.Thread(target=self._poll_nvml, daemon=True)
+            self.thread.start()
+            return
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
                                           "--format=csv,noheader,nounits", "-lms", "100"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread = threading.Thread(target=self._read_smi, daemon=True)
             self.thread.start()
         except OSError:
             self.proc = None
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
-
     def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
+        if not self.thread:
+            return {"sm_mhz": None, "sm_max_mhz": None, "samples": 0, "reasons": ["nvml and nvidia-smi unavailable"]}
+        self.stop_flag.set()
+        if self.proc:
+            self.proc.terminate()
         self.thread.join(timeout=2)
-        sm, mx, reasons = [], None, set()
-        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
-        for r in self.rows:
-            try:
-                sm.append(float(r[0]))
-                mx = float(r[1])
-            except (ValueError, IndexError):
-                continue
-            for name, v in zip(names, r[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        sm.sort()
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "samples": len(sm),
-                "reasons": sorted(reasons)}
+        sm = sorted(r[0] for r in self.rows)
+        reasons = set().union(*[r[2] for r in self.rows]) if self.rows else set()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": self.rows[-1][1] if self.rows else None,
+                "samples": len(sm), "source": "nvml" if self.nvml else "nvidia-smi", "reasons": sorted(reasons)}
 
 
 def measured_peak():

@@ -121,6 +121,7 @@ struct Reducer {
 // The small levels of the hierarchy (<= kTailCells cells each) are cycled by ONE block in one launch
 // (k_tail_cycle): by value, so the kernel needs no indirection to find its arrays.
 constexpr int kTailMaxLevels = 8, kTailCells = 1024, kTailThreads = 1024;
+constexpr size_t kTailMaxSmem = 160 * 1024;   // iterates, residuals and right-hand sides of all tail levels (33 KB for 32x32)
 struct TailLevel {
     Coarse9 op;
     Weights w;            // to the next coarser level (unused on the last)
@@ -160,6 +161,7 @@ struct Solver {
     int nu_fine = 1, nu_coarse = 2, nu_deep = 2;   // sweeps: fine, level 1, levels >= 2
     int tail_top = -1;                             // first level cycled by k_tail_cycle (-1: none)
     TailArgs tail{};
+    size_t tail_smem = 0;                          // dynamic shared memory of k_tail_cycle
     int w_lo = 1, w_hi = 0;                        // levels visited twice per cycle (empty range: V-cycle)
     bool have_solution = false;    // x holds the pressure of the last solve
     bool have_hierarchy = false;   // conductances and multigrid operators of the last solve are in place

@@ -550,126 +550,190 @@ k_restrict(Weights w, const double *__restrict__ r, int nz, int nx, double *__re
 }
 
 // ------------------------------------------------------------------------------- the tail levels
-// One colour of Gauss-Seidel on a whole (small) level, in place, by one block.
-__device__ __forceinline__ void tail_gs_colour(const C9 &A, const double *b, double *x, int cz, int cx)
+// Operator row of one cell of a tail level, in registers while the level is being smoothed: couplings
+// in the order the sums run (SW, S, SE, W, E, NW, N, NE; 0 where the neighbour is absent), diagonal, and
+// the absorption part S of the difference-form residual.
+struct TailCell {
+    double gsw, gs, gse, gw, ge, gnw, gn, gne, diag, S;
+};
+__device__ __forceinline__ TailCell tail_load_cell(const Coarse9 &v, int z, int x)
 {
-    const int nz = A.nz(), nx = A.nx();
-    const int hz = (nz - cz + 1) / 2, hx = (nx - cx + 1) / 2;
-    for (int k = threadIdx.x; k < hz * hx; k += blockDim.x) {
-        const int z = 2 * (k / hx) + cz, xx = 2 * (k % hx) + cx;
-        const int i = z * nx + xx;
-        double s = b[i];
-#pragma unroll
-        for (int dz = -1; dz <= 1; dz++)
-#pragma unroll
-            for (int dx = -1; dx <= 1; dx++) {
-                if (dz == 0 && dx == 0) continue;
-                const int qz = z + dz, qx = xx + dx;
-                if (qz < 0 || qz >= nz || qx < 0 || qx >= nx) continue;
-                s += A.g(z, xx, dz, dx) * x[qz * nx + qx];
-            }
-        x[i] = s / A.diag(z, xx);
+    TailCell c{0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 1.0, 0.0};
+    const int nx = v.nx, i = z * nx + x;
+    const bool xm = x > 0, xp = x + 1 < nx, zm = z > 0;
+    c.ge = v.E[i];                            // E, N, NE, NW are stored 0 where the neighbour is absent
+    c.gn = v.N[i];
+    c.gne = v.NE[i];
+    c.gnw = v.NW[i];
+    if (xm) c.gw = v.E[i - 1];
+    if (zm) {
+        c.gs = v.N[i - nx];
+        if (xm) c.gsw = v.NE[i - nx - 1];
+        if (xp) c.gse = v.NW[i - nx + 1];
     }
+    c.diag = v.C[i];
+    c.S = v.S[i];
+    return c;
+}
+// one Gauss-Seidel update of the cell at p (row pitch W, zero frame around the level)
+__device__ __forceinline__ void tail_relax(const TailCell &c, double b, double *p, int W)
+{
+    double s = b;
+    s += c.gsw * p[-W - 1];
+    s += c.gs * p[-W];
+    s += c.gse * p[-W + 1];
+    s += c.gw * p[-1];
+    s += c.ge * p[1];
+    s += c.gnw * p[W - 1];
+    s += c.gn * p[W];
+    s += c.gne * p[W + 1];
+    p[0] = s / c.diag;
 }
 
 // All levels of at most kTailCells cells -- 32x32 and below -- in ONE launch by ONE block: the whole
 // sub-cycle (pre-smoothing, residual, restriction, ..., dense solve, ..., prolongation, post-smoothing)
 // with block barriers where the per-level kernels had launch boundaries.  These levels hold a few
-// hundred cells: their cost was pure launch latency (about 16 launches per visit, several visits per
-// cycle with the W-levels above them).  Here a level is one tile, so the smoother is exact four-colour
-// Gauss-Seidel, backward on the way up: the cycle stays symmetric.
+// hundred cells: their cost is pure latency (about 16 launches per visit as separate kernels, several
+// visits per cycle with the W-levels above them).  A level is one tile, so the smoother is exact
+// four-colour Gauss-Seidel, backward on the way up: the cycle stays symmetric.
+// Thread t owns cell t of every level.  The iterates, right-hand sides and residuals of all tail levels
+// live in shared memory (iterates and residuals inside a one-cell frame of zeros, so no pass has
+// neighbour logic); a thread fetches its operator row, its restriction or interpolation weights and
+// its right-hand side with independent loads at the head of each level visit and the colour passes then
+// run on registers and shared memory.  One visit of a level costs one L2 round trip instead of one per
+// pass (measured at 8192^2: 50 -> see profiles/README.md us per launch).
 // rhs in lv[0].b; result in lv[0].r (zero_init == 0: lv[0].r is the initial guess).
 __global__ void __launch_bounds__(kTailThreads)
 k_tail_cycle(TailArgs a, int zero_init, const PcgState *st)
 {
     if (stopped(st)) return;
     const int tid = threadIdx.x, T = blockDim.x;
-    __shared__ double sb[64];
-    // (Measured: staging the ~130 KB these levels need in shared memory first is slower than reading
-    // them through L1/L2 phase by phase -- 4.09 vs 3.76 ms for a 1024^2 solve.)
+    LCL_DYNAMIC_SMEM(double, smem);
+    // shared-memory map: framed iterate X_l and framed residual R_l per level, then the right-hand sides
+    int offX[kTailMaxLevels], offB[kTailMaxLevels];
+    int framed = 0, plain = 0;
+    for (int l = 0; l < a.nlev; l++) {
+        offX[l] = framed;
+        offB[l] = plain;
+        framed += (a.lv[l].op.nz + 2) * (a.lv[l].op.nx + 2);
+        plain += a.lv[l].op.nz * a.lv[l].op.nx;
+    }
+    double *SX = smem, *SR = smem + framed, *SB = smem + 2 * framed;
+    for (int i = tid; i < 2 * framed; i += T) smem[i] = 0.0;
+    __syncthreads();
+
     for (int l = 0; l + 1 < a.nlev; l++) {
         const TailLevel &L = a.lv[l], &Cc = a.lv[l + 1];
-        const C9 A{L.op};
-        const int nz = L.op.nz, nx = L.op.nx, n = nz * nx, nzc = Cc.op.nz, nxc = Cc.op.nx;
-        for (int i = tid; i < n; i += T) L.x[i] = (l > 0 || zero_init) ? 0.0 : L.r[i];
+        const int nz = L.op.nz, nx = L.op.nx, n = nz * nx, nzc = Cc.op.nz, nxc = Cc.op.nx, W = nx + 2;
+        const bool own = tid < n;
+        const int z = own ? tid / nx : 0, xx = own ? tid % nx : 0;
+        double *X = SX + offX[l], *R = SR + offX[l], *B = SB + offB[l];
+        double *p = X + (z + 1) * W + xx + 1;
+        TailCell c{};
+        double b = 0.0;
+        if (own) {
+            c = tail_load_cell(L.op, z, xx);
+            b = l == 0 ? L.b[tid] : B[tid];
+            if (l == 0) B[tid] = b;
+            if (l == 0 && !zero_init) *p = L.r[tid];
+        }
+        // restriction weights of the coarse point this thread owns (0 where the fine neighbour is absent)
+        const bool cown = tid < nzc * nxc;
+        double whw = 0.0, whe = 0.0, wvs = 0.0, wvn = 0.0, wsw = 0.0, wse = 0.0, wnw = 0.0, wne = 0.0;
+        const int Z = cown ? tid / nxc : 0, Xc = cown ? tid % nxc : 0;
+        if (cown) {
+            const int k = tid;
+            const bool xm = Xc > 0, xp = 2 * Xc + 1 < nx, zm = Z > 0, zp = 2 * Z + 1 < nz;
+            if (xp) whw = L.w.hw[k];
+            if (xm) whe = L.w.he[k - 1];
+            if (zp) wvs = L.w.vs[k];
+            if (zm) wvn = L.w.vn[k - nxc];
+            if (zp && xp) wsw = L.w.csw[k];
+            if (zp && xm) wse = L.w.cse[k - 1];
+            if (zm && xp) wnw = L.w.cnw[k - nxc];
+            if (zm && xm) wne = L.w.cne[k - nxc - 1];
+        }
+        const int colour = 2 * (z & 1) + (xx & 1);
         __syncthreads();
         for (int sweep = 0; sweep < a.nu; sweep++)
             for (int col = 0; col < 4; col++) {
-                tail_gs_colour(A, L.b, L.x, col >> 1, col & 1);
+                if (own && colour == col) tail_relax(c, b, p, W);
                 __syncthreads();
             }
-        for (int i = tid; i < n; i += T) {   // residual, difference form
-            const int z = i / nx, xx = i % nx;
-            const double xi = L.x[i];
-            double s = L.b[i] - A.S(z, xx) * xi;
-#pragma unroll
-            for (int dz = -1; dz <= 1; dz++)
-#pragma unroll
-                for (int dx = -1; dx <= 1; dx++) {
-                    if (dz == 0 && dx == 0) continue;
-                    const int qz = z + dz, qx = xx + dx;
-                    if (qz < 0 || qz >= nz || qx < 0 || qx >= nx) continue;
-                    s -= A.g(z, xx, dz, dx) * (xi - L.x[qz * nx + qx]);
-                }
-            L.r[i] = s;
+        if (own) {   // residual, difference form
+            const double xi = *p;
+            double s = b - c.S * xi;
+            s -= c.gsw * (xi - p[-W - 1]);
+            s -= c.gs * (xi - p[-W]);
+            s -= c.gse * (xi - p[-W + 1]);
+            s -= c.gw * (xi - p[-1]);
+            s -= c.ge * (xi - p[1]);
+            s -= c.gnw * (xi - p[W - 1]);
+            s -= c.gn * (xi - p[W]);
+            s -= c.gne * (xi - p[W + 1]);
+            R[(z + 1) * W + xx + 1] = s;
         }
         __syncthreads();
-        for (int k = tid; k < nzc * nxc; k += T) {   // restriction, as k_restrict
-            const int Z = k / nxc, X = k % nxc;
-            const int z = 2 * Z, x = 2 * X, i = z * nx + x;
-            const bool xm = X > 0, xp = x + 1 < nx, zm = Z > 0, zp = z + 1 < nz;
-            const double *r = L.r;
-            double s = r[i];
-            if (xp) s += L.w.hw[k] * r[i + 1];
-            if (xm) s += L.w.he[k - 1] * r[i - 1];
-            if (zp) s += L.w.vs[k] * r[i + nx];
-            if (zm) s += L.w.vn[k - nxc] * r[i - nx];
-            if (zp && xp) s += L.w.csw[k] * r[i + nx + 1];
-            if (zp && xm) s += L.w.cse[k - 1] * r[i + nx - 1];
-            if (zm && xp) s += L.w.cnw[k - nxc] * r[i - nx + 1];
-            if (zm && xm) s += L.w.cne[k - nxc - 1] * r[i - nx - 1];
-            Cc.b[k] = s;
+        if (cown) {   // restriction, as k_restrict
+            const double *r = R + (2 * Z + 1) * W + 2 * Xc + 1;
+            double s = r[0];
+            s += whw * r[1];
+            s += whe * r[-1];
+            s += wvs * r[W];
+            s += wvn * r[-W];
+            s += wsw * r[W + 1];
+            s += wse * r[W - 1];
+            s += wnw * r[-W + 1];
+            s += wne * r[-W - 1];
+            SB[offB[l + 1] + tid] = s;
         }
         __syncthreads();
     }
     {   // last level: x = S inv S b
-        const TailLevel &L = a.lv[a.nlev - 1];
-        const int n = L.op.nz * L.op.nx;
-        for (int i = tid; i < n; i += T) sb[i] = a.scale[i] * L.b[i];
+        const int l = a.nlev - 1;
+        const TailLevel &L = a.lv[l];
+        const int nx = L.op.nx, n = L.op.nz * nx, W = nx + 2;
+        double *X = SX + offX[l], *B = SB + offB[l];
+        __shared__ double sb[64];
+        for (int i = tid; i < n; i += T) sb[i] = a.scale[i] * B[i];
         __syncthreads();
         for (int i = tid; i < n; i += T) {
             double s = 0.0;
             for (int j = 0; j < n; j++) s += a.inv[i * n + j] * sb[j];
-            L.r[i] = a.scale[i] * s;
+            X[(i / nx + 1) * W + i % nx + 1] = a.scale[i] * s;
         }
         __syncthreads();
     }
     for (int l = a.nlev - 2; l >= 0; l--) {
         const TailLevel &L = a.lv[l], &Cc = a.lv[l + 1];
-        const C9 A{L.op};
-        const int nz = L.op.nz, nx = L.op.nx, n = nz * nx, nzc = Cc.op.nz, nxc = Cc.op.nx;
-        const double *e = Cc.r;
-        for (int k = tid; k < nzc * nxc; k += T) {   // x += P e, thread per coarse block
-            const int Z = k / nxc, X = k % nxc;
-            const int i = 2 * Z * nx + 2 * X;
-            const bool xp = 2 * X + 1 < nx, zp = 2 * Z + 1 < nz, Xp = X + 1 < nxc, Zp = Z + 1 < nzc;
-            const double e00 = e[k];
-            const double e01 = Xp ? e[k + 1] : 0.0;
-            const double e10 = Zp ? e[k + nxc] : 0.0;
-            const double e11 = (Zp && Xp) ? e[k + nxc + 1] : 0.0;
-            L.x[i] += e00;
-            if (xp) L.x[i + 1] += L.w.hw[k] * e00 + L.w.he[k] * e01;
-            if (zp) L.x[i + nx] += L.w.vs[k] * e00 + L.w.vn[k] * e10;
-            if (zp && xp) L.x[i + nx + 1] += (L.w.csw[k] * e00 + L.w.cse[k] * e01) + (L.w.cnw[k] * e10 + L.w.cne[k] * e11);
+        const int nz = L.op.nz, nx = L.op.nx, n = nz * nx, nxc = Cc.op.nx, W = nx + 2, Wc = nxc + 2;
+        const bool own = tid < n;
+        const int z = own ? tid / nx : 0, xx = own ? tid % nx : 0;
+        double *X = SX + offX[l];
+        double *p = X + (z + 1) * W + xx + 1;
+        TailCell c{};
+        double b = 0.0;
+        if (own) {
+            c = tail_load_cell(L.op, z, xx);
+            b = SB[offB[l] + tid];
+            // x += P e for this cell: e sits framed in the coarse level's iterate
+            const int k = (z >> 1) * nxc + (xx >> 1);
+            const double *e = SX + offX[l + 1] + ((z >> 1) + 1) * Wc + (xx >> 1) + 1;
+            const double e00 = e[0], e01 = e[1], e10 = e[Wc], e11 = e[Wc + 1];
+            double pe;
+            if (!(z & 1)) pe = !(xx & 1) ? e00 : L.w.hw[k] * e00 + L.w.he[k] * e01;
+            else if (!(xx & 1)) pe = L.w.vs[k] * e00 + L.w.vn[k] * e10;
+            else pe = (L.w.csw[k] * e00 + L.w.cse[k] * e01) + (L.w.cnw[k] * e10 + L.w.cne[k] * e11);
+            *p += pe;
         }
+        const int colour = 2 * (z & 1) + (xx & 1);
         __syncthreads();
         for (int sweep = 0; sweep < a.nu; sweep++)
             for (int col = 3; col >= 0; col--) {
-                tail_gs_colour(A, L.b, L.x, col >> 1, col & 1);
+                if (own && colour == col) tail_relax(c, b, p, W);
                 __syncthreads();
             }
-        for (int i = tid; i < n; i += T) L.r[i] = L.x[i];
-        __syncthreads();
+        if (l == 0 && own) L.r[tid] = *p;
     }
 }
 
@@ -734,6 +798,7 @@ static int leg_grid(Solver &s, int tz, int tx)
     if (!s.down_configured) {   // per device: the attribute lives in the context of the solver's GPU
         CUDA_CHECK(cudaFuncSetAttribute(k_down5, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDnSmem));
         CUDA_CHECK(cudaFuncSetAttribute(k_up5, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kUpSmem));
+        CUDA_CHECK(cudaFuncSetAttribute(k_tail_cycle, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTailMaxSmem));
         s.down_configured = true;
     }
     const long long tiles = (long long)div_up(s.nx, tx) * div_up(s.nz, tz);
@@ -840,7 +905,7 @@ void mg_vcycle(Solver &s, const double *r, double *ztmp, double *zout, PcgState 
     std::function<void(size_t, bool)> cycle = [&](size_t l, bool zero_init) {
         Level &f = s.levels[l];
         if ((int)l == s.tail_top) {   // this level and everything below it: one block, one launch
-            LAUNCH(k_tail_cycle, 1, kTailThreads, 0, s.stream, s.tail, zero_init ? 1 : 0, (const PcgState *)st);
+            LAUNCH(k_tail_cycle, 1, kTailThreads, s.tail_smem, s.stream, s.tail, zero_init ? 1 : 0, (const PcgState *)st);
             return;
         }
         if (l == nlev - 1) {   // coarsest: dense solve

@@ -302,7 +302,13 @@ void mg_allocate(Solver &s)
         const size_t nlev = s.levels.size();
         size_t top = 1;
         while (top < nlev && s.levels[top].n > (size_t)kTailCells) top++;
-        if (top + 1 < nlev && nlev - top <= (size_t)kTailMaxLevels && s.coarse_n <= 64) {
+        size_t framed = 0, plain = 0;
+        for (size_t l = top; l < nlev; l++) {
+            framed += (size_t)(s.levels[l].nz + 2) * (s.levels[l].nx + 2);
+            plain += s.levels[l].n;
+        }
+        s.tail_smem = (2 * framed + plain) * sizeof(double);
+        if (top + 1 < nlev && nlev - top <= (size_t)kTailMaxLevels && s.coarse_n <= 64 && s.tail_smem <= kTailMaxSmem) {
             s.tail_top = (int)top;
             s.tail.nlev = (int)(nlev - top);
             for (size_t l = top; l < nlev; l++) {

@@ -16,6 +16,11 @@ namespace lcl {
 
 thread_local std::string g_last_error;
 thread_local long long g_launches = 0;
+bool use_pdl()
+{
+    static const bool on = getenv("APM_LCL_NO_PDL") == nullptr;
+    return on;
+}
 
 static bool is_device_ptr(const void *p)
 {

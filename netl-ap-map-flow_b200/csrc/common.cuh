@@ -21,6 +21,7 @@ namespace lcl {
 // error handling / launch accounting (thread local: one solver per host thread is the model)
 extern thread_local std::string g_last_error;
 extern thread_local long long g_launches;
+bool use_pdl();   // api.cu: programmatic dependent launches unless APM_LCL_NO_PDL is set
 
 struct CudaError {
     std::string msg;
@@ -43,12 +44,36 @@ inline void cuda_check(cudaError_t e, const char *what, const char *file, int li
         ++::lcl::g_launches;                                                 \
         CUDA_CHECK(cudaGetLastError());                                      \
     } while (0)
+// Launch of a kernel of the PCG iteration: allowed to start while its predecessor in the stream drains
+// (programmatic dependent launch; the kernel waits in stopped() -> cudaGridDependencySynchronize() before
+// it touches memory).  The ~90 launches of an iteration are short dependent kernels on the coarse levels:
+// what this hides is their scheduling latency.  APM_LCL_NO_PDL=1 falls back to plain launches.
+#define LAUNCH_DEP(kernel, grid_, block_, smem_, stream_, ...)                              \
+    do {                                                                                      \
+        if (::lcl::use_pdl()) {                                                               \
+            cudaLaunchConfig_t cfg_ = {};                                                     \
+            cfg_.gridDim = dim3(grid_);                                                       \
+            cfg_.blockDim = dim3(block_);                                                     \
+            cfg_.dynamicSmemBytes = (smem_);                                                  \
+            cfg_.stream = (stream_);                                                          \
+            cudaLaunchAttribute attr_[1];                                                     \
+            attr_[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;                 \
+            attr_[0].val.programmaticStreamSerializationAllowed = 1;                          \
+            cfg_.attrs = attr_;                                                               \
+            cfg_.numAttrs = 1;                                                                \
+            CUDA_CHECK(cudaLaunchKernelEx(&cfg_, kernel, __VA_ARGS__));                       \
+            ++::lcl::g_launches;                                                              \
+        } else {                                                                              \
+            LAUNCH(kernel, grid_, block_, smem_, stream_, __VA_ARGS__);                       \
+        }                                                                                     \
+    } while (0)
 #else
 #define LAUNCH(kernel, grid, block, smem, stream, ...)                                        \
     do {                                                                                      \
         ::cusim::launch(dim3(grid), dim3(block), (smem), [&]() { kernel(__VA_ARGS__); });     \
         ++::lcl::g_launches;                                                                  \
     } while (0)
+#define LAUNCH_DEP LAUNCH
 #endif
 
 inline int div_up(long long a, long long b) { return (int)((a + b - 1) / b); }

@@ -15,7 +15,15 @@
 
 namespace lcl {
 
-__device__ __forceinline__ bool stopped(const PcgState *st) { return st && (st->converged | st->failed); }
+// First statement of every kernel of the iteration: wait for the predecessor (a no-op unless the kernel was
+// launched as a programmatic dependent, LAUNCH_DEP), then the device-side stop flag.
+__device__ __forceinline__ bool stopped(const PcgState *st)
+{
+#ifndef LCL_CPU_SIM
+    cudaGridDependencySynchronize();
+#endif
+    return st && (st->converged | st->failed);
+}
 
 // -------------------------------------------------------------------------------- coarse levels
 __global__ void __launch_bounds__(kBlock)
@@ -67,87 +75,167 @@ __device__ __forceinline__ double prolong_value(const Weights &w, const double *
 constexpr int kSmTZ = 16, kSmTX = 64;   // smoother tile: 1024 points, 256 threads
 constexpr int kSmThreads = 256;         // compile-time so the per-tile loops unroll and batch their loads
 
-// sx (H x W doubles, H and W even) covers the fine cells from (zr, xr), both even (possibly -2).
-// sx := x + P e over the same framed region, in one pass: the thread that owns a coarse 2x2 block loads
-// its four x values together with the weights and coarse values (all loads independent, in flight
-// together) and writes the block once -- no read-modify-write of shared memory, no extra barrier.
-template <int H, int W>
-__device__ __forceinline__ void load_prolonged(double *sx, const double *__restrict__ xin, const Weights &w,
-                                               const double *__restrict__ e, int nzc, int nxc, int zr, int xr, int nz,
-                                               int nx)
-{
-    constexpr int BH = H / 2, BW = W / 2;
-    const int bz0 = zr >> 1, bx0 = xr >> 1;   // arithmetic shift: -2 >> 1 == -1
-    #pragma unroll
-    for (int k = threadIdx.x; k < BH * BW; k += kSmThreads) {
-        const int bzl = k / BW, bxl = k % BW;
-        const int bz = bz0 + bzl, bx = bx0 + bxl;
-        double v00 = 0.0, v01 = 0.0, v10 = 0.0, v11 = 0.0;
-        if (bz >= 0 && bx >= 0 && bz < nzc && bx < nxc) {
-            const size_t b = (size_t)bz * nxc + bx;
-            const size_t i = (size_t)(2 * bz) * nx + 2 * bx;
-            const bool Xp = bx + 1 < nxc, Zp = bz + 1 < nzc;
-            const bool xp = 2 * bx + 1 < nx, zp = 2 * bz + 1 < nz;
-            const double e00 = e[b];
-            const double e01 = Xp ? e[b + 1] : 0.0;
-            const double e10 = Zp ? e[b + nxc] : 0.0;
-            const double e11 = (Zp && Xp) ? e[b + nxc + 1] : 0.0;
-            v00 = xin[i] + e00;
-            if (xp) v01 = xin[i + 1] + (w.hw[b] * e00 + w.he[b] * e01);
-            if (zp) v10 = xin[i + nx] + (w.vs[b] * e00 + w.vn[b] * e10);
-            if (zp && xp) v11 = xin[i + nx + 1] + ((w.csw[b] * e00 + w.cse[b] * e01) + (w.cnw[b] * e10 + w.cne[b] * e11));
-        }
-        double *p = &sx[(2 * bzl) * W + 2 * bxl];           // even offset: 16-byte aligned
-        *reinterpret_cast<double2 *>(p) = make_double2(v00, v01);
-        *reinterpret_cast<double2 *>(p + W) = make_double2(v10, v11);
-    }
-}
-
 // Everything one cell of a 9-point level needs for a Gauss-Seidel update, held in registers for the
 // whole launch: the 8 couplings (W, E, S, N, SW, SE, NW, NE), the right-hand side and 1/diag.  Cells
 // outside the grid get all zeros, so their "update" is 0 and the sweeps need no bounds checks.
 struct Cell9 {
     double gw, ge, gs, gn, gsw, gse, gnw, gne, b, inv;
 };
-__device__ __forceinline__ Cell9 load_cell9(const Coarse9 &v, const double *__restrict__ b, int z, int x)
-{
-    Cell9 c{0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
-    const int nx = v.nx;
-    if (z < v.nz && x < nx) {
-        const size_t i = (size_t)z * nx + x;
-        const bool xm = x > 0, xp = x + 1 < nx, zm = z > 0;
-        c.ge = v.E[i];                       // E, N, NE, NW are stored 0 where the neighbour is absent
-        c.gn = v.N[i];
-        c.gne = v.NE[i];
-        c.gnw = v.NW[i];
-        if (xm) c.gw = v.E[i - 1];
-        if (zm) {
-            c.gs = v.N[i - nx];
-            if (xm) c.gsw = v.NE[i - nx - 1];
-            if (xp) c.gse = v.NW[i - nx + 1];
-        }
-        c.b = b[i];
-        c.inv = 1.0 / v.C[i];
-    }
-    return c;
-}
+// Shared-memory layout of a framed row of x (and of the staged operator rows): the even columns first,
+// then the odd ones.  A thread owns a 2x2 block, so the lanes of a warp touch columns of ONE parity at
+// stride 2: split by parity they are consecutive doubles -- conflict-free, half the wavefronts of the
+// plain row (the sweeps were shared-memory bound: 72 % l1tex, 57 M wavefronts per level-1 launch).
 template <int W>
-__device__ __forceinline__ void relax9(const Cell9 &c, double *p)
+__device__ __forceinline__ int split_pos(int row, int col) { return row * W + (col >> 1) + (col & 1) * (W / 2); }
+
+// pc: the cell; pw / pe: its west / east neighbour in the same row (all three in the split layout)
+template <int W>
+__device__ __forceinline__ void relax9(const Cell9 &c, double *pc, const double *pw, const double *pe)
 {
     double s = c.b;
-    s += c.gw * p[-1] + c.ge * p[1];
-    s += c.gs * p[-W] + c.gn * p[W];
-    s += c.gsw * p[-W - 1] + c.gse * p[-W + 1];
-    s += c.gnw * p[W - 1] + c.gne * p[W + 1];
-    p[0] = s * c.inv;
+    s += c.gw * pw[0] + c.ge * pe[0];
+    s += c.gs * pc[-W] + c.gn * pc[W];
+    s += c.gsw * pw[-W] + c.gse * pe[-W];
+    s += c.gnw * pw[W] + c.gne * pe[W];
+    pc[0] = s * c.inv;
+}
+
+// Operator staging of the 9-point smoother: the rows a 16x64 tile needs -- E, N, NE, NW of the tile plus
+// the row below and one column either side (rows z0-1..z0+15, columns x0-1..x0+64), b and C of the tile
+// itself -- copied asynchronously into shared memory, zero-filled outside the grid.
+constexpr int kStRows = kSmTZ + 1, kStCols = kSmTX + 2, kStPlane = kStRows * kStCols, kStTile = kSmTZ * kSmTX;
+constexpr int kSmW = kSmTX + 4, kSmH = kSmTZ + 4;   // x with a 2-cell frame: the region stays aligned to coarse blocks
+constexpr size_t kSm9Smem = (size_t)(4 * kStPlane + 2 * kStTile + kSmH * kSmW) * sizeof(double);
+static_assert(2 * (kSm9Smem + 1024) <= 227 * 1024, "two blocks per SM");
+
+__device__ __forceinline__ void stage_tile9(double *st, const Coarse9 &v, const double *__restrict__ b, int z0, int x0)
+{
+    const int nz = v.nz, nx = v.nx;
+    double *sE = st, *sN = st + kStPlane, *sNE = st + 2 * kStPlane, *sNW = st + 3 * kStPlane;
+    double *sb = st + 4 * kStPlane, *sC = sb + kStTile;
+#pragma unroll 2
+    for (int k = threadIdx.x; k < kStPlane; k += kSmThreads) {
+        const int r = k / kStCols, cc = k % kStCols;
+        const int z = z0 - 1 + r, x = x0 - 1 + cc, q = split_pos<kStCols>(r, cc);
+        const bool in = z >= 0 && z < nz && x >= 0 && x < nx;
+        const size_t i = in ? (size_t)z * nx + x : 0;
+        cp_async8(&sE[q], v.E + i, in);
+        cp_async8(&sN[q], v.N + i, in);
+        cp_async8(&sNE[q], v.NE + i, in);
+        cp_async8(&sNW[q], v.NW + i, in);
+    }
+#pragma unroll
+    for (int k = threadIdx.x; k < kStTile; k += kSmThreads) {
+        const int lz = k / kSmTX, lx = k % kSmTX;
+        const int z = z0 + lz, x = x0 + lx, q = split_pos<kSmTX>(lz, lx);
+        const bool in = z < nz && x < nx;
+        const size_t i = in ? (size_t)z * nx + x : 0;
+        cp_async8(&sb[q], b + i, in);
+        cp_async8(&sC[q], v.C + i, in);
+    }
+}
+// the staged operator row of tile cell (lz, lx): every coupling a neighbour outside the grid would carry is
+// either stored as 0 (E, N, NE, NW where the neighbour is absent) or zero-filled by the staging
+__device__ __forceinline__ Cell9 staged_cell9(const double *st, int lz, int lx)
+{
+    const double *sE = st, *sN = st + kStPlane, *sNE = st + 2 * kStPlane, *sNW = st + 3 * kStPlane;
+    const double *sb = st + 4 * kStPlane, *sC = sb + kStTile;
+    const int r = lz + 1, cc = lx + 1;
+    const int k = split_pos<kStCols>(r, cc), kw = split_pos<kStCols>(r, cc - 1), ke = split_pos<kStCols>(r, cc + 1);
+    Cell9 c;
+    c.ge = sE[k];
+    c.gn = sN[k];
+    c.gne = sNE[k];
+    c.gnw = sNW[k];
+    c.gw = sE[kw];
+    c.gs = sN[k - kStCols];
+    c.gsw = sNE[kw - kStCols];
+    c.gse = sNW[ke - kStCols];
+    c.b = sb[split_pos<kSmTX>(lz, lx)];
+    const double d = sC[split_pos<kSmTX>(lz, lx)];
+    c.inv = d != 0.0 ? 1.0 / d : 0.0;          // cells outside the grid: everything 0, their "update" is 0
+    return c;
+}
+
+// Second stage, up leg only: what x + P e of the framed tile needs -- x over the framed region, the coarse
+// values e of its (H/2+1) x (W/2+1) blocks and the eight weight planes of its H/2 x W/2 blocks.
+constexpr int kPrBH = kSmH / 2, kPrBW = kSmW / 2, kPrE = (kPrBH + 1) * (kPrBW + 1), kPrB = kPrBH * kPrBW;
+constexpr int kPrStage = kSmH * kSmW + kPrE + 8 * kPrB;
+constexpr size_t kSm9SmemUp = kSm9Smem + (size_t)(kPrStage + (kPrStage & 1)) * sizeof(double);
+static_assert(2 * (kSm9SmemUp + 1024) <= 227 * 1024, "two blocks per SM");
+
+__device__ __forceinline__ void stage_prolong9(double *st, const double *__restrict__ xin, const Weights &w,
+                                               const double *__restrict__ e, int nzc, int nxc, int z0, int x0, int nz,
+                                               int nx)
+{
+    double *sXin = st, *sE = st + kSmH * kSmW, *sW = sE + kPrE;
+    const int zr = z0 - 2, xr = x0 - 2, bz0 = zr >> 1, bx0 = xr >> 1;   // arithmetic shift: -2 >> 1 == -1
+#pragma unroll 2
+    for (int k = threadIdx.x; k < kSmH * kSmW; k += kSmThreads) {
+        const int z = zr + k / kSmW, x = xr + k % kSmW;
+        const bool in = z >= 0 && z < nz && x >= 0 && x < nx;
+        cp_async8(&sXin[k], xin + (in ? (size_t)z * nx + x : 0), in);
+    }
+    for (int k = threadIdx.x; k < kPrE; k += kSmThreads) {
+        const int bz = bz0 + k / (kPrBW + 1), bx = bx0 + k % (kPrBW + 1);
+        const bool in = bz >= 0 && bz < nzc && bx >= 0 && bx < nxc;
+        cp_async8(&sE[k], e + (in ? (size_t)bz * nxc + bx : 0), in);
+    }
+#pragma unroll
+    for (int k = threadIdx.x; k < kPrB; k += kSmThreads) {
+        const int bz = bz0 + k / kPrBW, bx = bx0 + k % kPrBW;
+        const bool in = bz >= 0 && bz < nzc && bx >= 0 && bx < nxc;
+        const size_t b = in ? (size_t)bz * nxc + bx : 0;
+        cp_async8(&sW[k], w.hw + b, in);
+        cp_async8(&sW[kPrB + k], w.he + b, in);
+        cp_async8(&sW[2 * kPrB + k], w.vs + b, in);
+        cp_async8(&sW[3 * kPrB + k], w.vn + b, in);
+        cp_async8(&sW[4 * kPrB + k], w.csw + b, in);
+        cp_async8(&sW[5 * kPrB + k], w.cse + b, in);
+        cp_async8(&sW[6 * kPrB + k], w.cnw + b, in);
+        cp_async8(&sW[7 * kPrB + k], w.cne + b, in);
+    }
+}
+// sx := x + P e over the framed region from the staged operands (one thread per coarse 2x2 block)
+__device__ __forceinline__ void prolong_staged9(double *sx, const double *st, int nzc, int nxc, int z0, int x0, int nz, int nx)
+{
+    constexpr int W = kSmW, BW = kPrBW, EW = kPrBW + 1;
+    const double *sXin = st, *sE = st + kSmH * kSmW, *sW = sE + kPrE;
+    const int bz0 = (z0 - 2) >> 1, bx0 = (x0 - 2) >> 1;
+#pragma unroll
+    for (int k = threadIdx.x; k < kPrB; k += kSmThreads) {
+        const int bzl = k / BW, bxl = k % BW;
+        const int bz = bz0 + bzl, bx = bx0 + bxl;
+        double v00 = 0.0, v01 = 0.0, v10 = 0.0, v11 = 0.0;
+        if (bz >= 0 && bx >= 0 && bz < nzc && bx < nxc) {
+            const bool xp = 2 * bx + 1 < nx, zp = 2 * bz + 1 < nz;
+            const double *ep = sE + bzl * EW + bxl;
+            const double e00 = ep[0], e01 = ep[1], e10 = ep[EW], e11 = ep[EW + 1];   // 0 beyond the coarse grid
+            const double *xi = sXin + (2 * bzl) * W + 2 * bxl;
+            v00 = xi[0] + e00;
+            if (xp) v01 = xi[1] + (sW[k] * e00 + sW[kPrB + k] * e01);
+            if (zp) v10 = xi[W] + (sW[2 * kPrB + k] * e00 + sW[3 * kPrB + k] * e10);
+            if (zp && xp)
+                v11 = xi[W + 1] + ((sW[4 * kPrB + k] * e00 + sW[5 * kPrB + k] * e01) + (sW[6 * kPrB + k] * e10 + sW[7 * kPrB + k] * e11));
+        }
+        double *p = &sx[(2 * bzl) * W + bxl];               // split rows: even column 2 bxl here, odd one W/2 further
+        p[0] = v00;
+        p[W / 2] = v01;
+        p[W] = v10;
+        p[W + W / 2] = v11;
+    }
 }
 
 // All four colours and all `nu` sweeps of one 9-point level in ONE launch.  Each block owns a
 // 16x64 tile, keeps x (+ frame) in shared memory and runs four-colour Gauss-Seidel on it; halo
 // values stay frozen during the launch (hybrid GS: Jacobi between tiles, GS inside -- a regular
 // splitting, and the backward variant is its transpose, so the cycle stays symmetric).  A thread
-// owns one 2x2 block (one cell of each colour) and loads its operator rows ONCE, all loads in
-// flight together; the sweeps then touch only registers and shared memory.
+// owns one 2x2 block (one cell of each colour) and holds its operator rows in registers; the sweeps
+// touch only registers and shared memory.  The rows reach the registers through a shared-memory stage
+// filled by asynchronous copies, and the copies for the block's NEXT tile are issued before the sweeps
+// of the current one start: the DRAM latency of a tile hides behind the sweeps and the store of the
+// tile before it (two resident blocks per SM could not hide it: 51 % of the copy peak before, see
+// profiles/README.md for after).
 // ZERO_INIT: x starts from 0 (down leg; nothing is read).  PROLONG: x starts from x + P e (up leg).
 template <bool ZERO_INIT, bool PROLONG, bool FORWARD>
 __global__ void __launch_bounds__(256, 2)
@@ -156,54 +244,70 @@ k_smooth9(Coarse9 v, const double *__restrict__ b, const double *__restrict__ xi
 {
     if (stopped(st)) return;
     const int nz = v.nz, nx = v.nx;
-    constexpr int W = kSmTX + 4, H = kSmTZ + 4;   // 2-cell frame keeps the region aligned to coarse blocks
-    alignas(16) __shared__ double sx[H * W];
+    constexpr int W = kSmW, H = kSmH;
+    LCL_DYNAMIC_SMEM(double, smem);
+    double *stage = smem, *sx = smem + 4 * kStPlane + 2 * kStTile;   // sx at a 16-byte aligned offset
+    double *stage2 = sx + kSmH * kSmW;                               // PROLONG only
     const int tiles_x = (nx + kSmTX - 1) / kSmTX, tiles_z = (nz + kSmTZ - 1) / kSmTZ;
+    const long long ntiles = (long long)tiles_x * tiles_z;
     const int tid = threadIdx.x;
     const int a = tid >> 5, c = tid & 31;
-    for (long long t = blockIdx.x; t < (long long)tiles_x * tiles_z; t += gridDim.x) {
+    if (blockIdx.x < ntiles) {
+        const int z0 = (int)(blockIdx.x / tiles_x) * kSmTZ, x0 = (int)(blockIdx.x % tiles_x) * kSmTX;
+        stage_tile9(stage, v, b, z0, x0);
+        if (PROLONG) stage_prolong9(stage2, xin, w, e, nzc, nxc, z0, x0, nz, nx);
+    }
+    for (long long t = blockIdx.x; t < ntiles; t += gridDim.x) {
         const int z0 = (int)(t / tiles_x) * kSmTZ, x0 = (int)(t % tiles_x) * kSmTX;
-        const int z = z0 + 2 * a, xx = x0 + 2 * c;
-        const Cell9 c00 = load_cell9(v, b, z, xx), c01 = load_cell9(v, b, z, xx + 1);
-        const Cell9 c10 = load_cell9(v, b, z + 1, xx), c11 = load_cell9(v, b, z + 1, xx + 1);
-        if (PROLONG) {
-            load_prolonged<H, W>(sx, xin, w, e, nzc, nxc, z0 - 2, x0 - 2, nz, nx);
-        } else {
+        if (!PROLONG) {
             for (int k = tid; k < H * W; k += kSmThreads) {
                 const int zf = z0 + k / W - 2, xf = x0 + k % W - 2;
                 double val = 0.0;
                 if (!ZERO_INIT && zf >= 0 && zf < nz && xf >= 0 && xf < nx)
                     val = xin[(size_t)zf * nx + xf];     // never the array this launch writes: other tiles read it
-                sx[k] = val;
+                sx[ZERO_INIT ? k : split_pos<W>(k / W, k % W)] = val;
             }
         }
+        cp_async_wait_all();
         __syncthreads();
-        double *p = &sx[(2 * a + 2) * W + 2 * c + 2];
+        const Cell9 c00 = staged_cell9(stage, 2 * a, 2 * c), c01 = staged_cell9(stage, 2 * a, 2 * c + 1);
+        const Cell9 c10 = staged_cell9(stage, 2 * a + 1, 2 * c), c11 = staged_cell9(stage, 2 * a + 1, 2 * c + 1);
+        if (PROLONG) prolong_staged9(sx, stage2, nzc, nxc, z0, x0, nz, nx);
+        __syncthreads();                                 // every operand is in registers or sx: the stages are free again
+        if (t + gridDim.x < ntiles) {
+            const long long tn = t + gridDim.x;
+            const int zn = (int)(tn / tiles_x) * kSmTZ, xn = (int)(tn % tiles_x) * kSmTX;
+            stage_tile9(stage, v, b, zn, xn);
+            if (PROLONG) stage_prolong9(stage2, xin, w, e, nzc, nxc, zn, xn, nz, nx);
+        }
+        // the thread's block: framed rows 2a+2, 2a+3, columns 2c+2 (even, half index c+1) and 2c+3 (odd)
+        double *pe0 = &sx[(2 * a + 2) * W + c + 1];      // even column
+        double *po0 = pe0 + W / 2;                       // odd column; west of the even one: po0 - 1, east of the odd one: pe0 + 1
         for (int sweep = 0; sweep < nu; sweep++) {
             if (FORWARD) {
-                relax9<W>(c00, p);
+                relax9<W>(c00, pe0, po0 - 1, po0);
                 __syncthreads();
-                relax9<W>(c01, p + 1);
+                relax9<W>(c01, po0, pe0, pe0 + 1);
                 __syncthreads();
-                relax9<W>(c10, p + W);
+                relax9<W>(c10, pe0 + W, po0 + W - 1, po0 + W);
                 __syncthreads();
-                relax9<W>(c11, p + W + 1);
+                relax9<W>(c11, po0 + W, pe0 + W, pe0 + W + 1);
                 __syncthreads();
             } else {
-                relax9<W>(c11, p + W + 1);
+                relax9<W>(c11, po0 + W, pe0 + W, pe0 + W + 1);
                 __syncthreads();
-                relax9<W>(c10, p + W);
+                relax9<W>(c10, pe0 + W, po0 + W - 1, po0 + W);
                 __syncthreads();
-                relax9<W>(c01, p + 1);
+                relax9<W>(c01, po0, pe0, pe0 + 1);
                 __syncthreads();
-                relax9<W>(c00, p);
+                relax9<W>(c00, pe0, po0 - 1, po0);
                 __syncthreads();
             }
         }
         for (int k = tid; k < kSmTZ * kSmTX; k += kSmThreads) {
             const int lz = k / kSmTX, lx = k % kSmTX;
             const int zf = z0 + lz, xf = x0 + lx;
-            if (zf < nz && xf < nx) xout[(size_t)zf * nx + xf] = sx[(lz + 2) * W + lx + 2];
+            if (zf < nz && xf < nx) xout[(size_t)zf * nx + xf] = sx[split_pos<W>(lz + 2, lx + 2)];
         }
         __syncthreads();
     }
@@ -799,6 +903,9 @@ static int leg_grid(Solver &s, int tz, int tx)
         CUDA_CHECK(cudaFuncSetAttribute(k_down5, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDnSmem));
         CUDA_CHECK(cudaFuncSetAttribute(k_up5, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kUpSmem));
         CUDA_CHECK(cudaFuncSetAttribute(k_tail_cycle, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTailMaxSmem));
+        CUDA_CHECK(cudaFuncSetAttribute(k_smooth9<true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSm9Smem));
+        CUDA_CHECK(cudaFuncSetAttribute(k_smooth9<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSm9Smem));
+        CUDA_CHECK(cudaFuncSetAttribute(k_smooth9<false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSm9SmemUp));
         s.down_configured = true;
     }
     const long long tiles = (long long)div_up(s.nx, tx) * div_up(s.nz, tz);
@@ -817,7 +924,7 @@ double bench_launch_cycle(Solver &s, const std::string &name)
     const double n = (double)s.n;
     auto tile_grid = [&](int nz, int nx) {
         long long tiles = (long long)div_up(nx, kSmTX) * div_up(nz, kSmTZ);
-        long long cap = (long long)s.num_sms * 6;
+        long long cap = (long long)s.num_sms * 2;   // persistent: two resident blocks per SM, each pipelining its tiles
         if (cap > kMaxPartials) cap = kMaxPartials;
         return (int)(tiles < cap ? tiles : cap);
     };
@@ -829,7 +936,7 @@ double bench_launch_cycle(Solver &s, const std::string &name)
     }
     if (name == "smooth9_l1" && s.levels.size() > 2) {
         Level &f = s.levels[1];
-        LAUNCH((k_smooth9<true, false, true>), tile_grid(f.nz, f.nx), kSmThreads, 0, s.stream, f.view9(), (const double *)f.b,
+        LAUNCH((k_smooth9<true, false, true>), tile_grid(f.nz, f.nx), kSmThreads, kSm9Smem, s.stream, f.view9(), (const double *)f.b,
                (const double *)nullptr, f.x, s.nu_coarse, Weights{}, (const double *)nullptr, 0, 0,
                (const PcgState *)s.state);
         return 56.0 * (double)f.n;   // b, C, E, N, NE, NW in; x out (couplings re-read from L1/L2 per sweep)
@@ -842,7 +949,7 @@ double bench_launch_cycle(Solver &s, const std::string &name)
     }
     if (name == "smooth9_l1_up" && s.levels.size() > 2) {
         Level &f = s.levels[1], &c = s.levels[2];
-        LAUNCH((k_smooth9<false, true, false>), tile_grid(f.nz, f.nx), kSmThreads, 0, s.stream, f.view9(), (const double *)f.b,
+        LAUNCH((k_smooth9<false, true, false>), tile_grid(f.nz, f.nx), kSmThreads, kSm9SmemUp, s.stream, f.view9(), (const double *)f.b,
                (const double *)f.x, f.r, s.nu_coarse, f.w, (const double *)c.r, c.nz, c.nx, (const PcgState *)s.state);
         return 64.0 * (double)f.n + (8.0 + 64.0) * (double)c.n;
     }
@@ -875,15 +982,15 @@ void mg_vcycle(Solver &s, const double *r, double *ztmp, double *zout, PcgState 
     const size_t nlev = s.levels.size();
     auto tile_grid = [&](int nz, int nx) {
         long long tiles = (long long)div_up(nx, kSmTX) * div_up(nz, kSmTZ);
-        long long cap = (long long)s.num_sms * 6;
+        long long cap = (long long)s.num_sms * 2;   // persistent: two resident blocks per SM, each pipelining its tiles
         if (cap > kMaxPartials) cap = kMaxPartials;
         return (int)(tiles < cap ? tiles : cap);
     };
 
     if (s.levels[0].w.hw == nullptr) {   // map small enough for the dense solve alone
         Level &c = s.levels[1];
-        LAUNCH(k_coarse_solve, 1, 64, c.n * sizeof(double), s.stream, s.coarse_inv, s.coarse_scale, r, zout, (int)c.n, st);
-        LAUNCH(k_dot_norms, 1, kBlock, 0, s.stream, r, (const double *)zout, v5, st, init, part, cnt);
+        LAUNCH_DEP(k_coarse_solve, 1, 64, c.n * sizeof(double), s.stream, s.coarse_inv, s.coarse_scale, r, zout, (int)c.n, st);
+        LAUNCH_DEP(k_dot_norms, 1, kBlock, 0, s.stream, r, (const double *)zout, v5, st, init, part, cnt);
         return;
     }
 
@@ -893,7 +1000,7 @@ void mg_vcycle(Solver &s, const double *r, double *ztmp, double *zout, PcgState 
     // zout doubles as the fine residual buffer in between.
     {   // whole fine down leg: smooth, residual, restriction
         Level &c = s.levels[1];
-        LAUNCH(k_down5, down_grid(s), kDnThreads, kDnSmem, s.stream, v5, s.levels[0].w, r, ztmp, c.b, c.nz, c.nx, st, init,
+        LAUNCH_DEP(k_down5, down_grid(s), kDnThreads, kDnSmem, s.stream, v5, s.levels[0].w, r, ztmp, c.b, c.nz, c.nx, st, init,
                part, cnt);
     }
     // Levels >= 1: cycle(l) solves level l approximately for the right-hand side in .b, result in .r.
@@ -905,31 +1012,31 @@ void mg_vcycle(Solver &s, const double *r, double *ztmp, double *zout, PcgState 
     std::function<void(size_t, bool)> cycle = [&](size_t l, bool zero_init) {
         Level &f = s.levels[l];
         if ((int)l == s.tail_top) {   // this level and everything below it: one block, one launch
-            LAUNCH(k_tail_cycle, 1, kTailThreads, s.tail_smem, s.stream, s.tail, zero_init ? 1 : 0, (const PcgState *)st);
+            LAUNCH_DEP(k_tail_cycle, 1, kTailThreads, s.tail_smem, s.stream, s.tail, zero_init ? 1 : 0, (const PcgState *)st);
             return;
         }
         if (l == nlev - 1) {   // coarsest: dense solve
-            LAUNCH(k_coarse_solve, 1, 64, f.n * sizeof(double), s.stream, s.coarse_inv, s.coarse_scale,
+            LAUNCH_DEP(k_coarse_solve, 1, 64, f.n * sizeof(double), s.stream, s.coarse_inv, s.coarse_scale,
                    (const double *)f.b, f.r, (int)f.n, st);
             return;
         }
         Level &c = s.levels[l + 1];
         const int nu = l == 1 ? s.nu_coarse : s.nu_deep;
         if (zero_init)
-            LAUNCH((k_smooth9<true, false, true>), tile_grid(f.nz, f.nx), kSmThreads, 0, s.stream, f.view9(),
+            LAUNCH_DEP((k_smooth9<true, false, true>), tile_grid(f.nz, f.nx), kSmThreads, kSm9Smem, s.stream, f.view9(),
                    (const double *)f.b, (const double *)nullptr, f.x, nu, now, (const double *)nullptr, 0, 0,
                    (const PcgState *)st);
         else
-            LAUNCH((k_smooth9<false, false, true>), tile_grid(f.nz, f.nx), kSmThreads, 0, s.stream, f.view9(),
+            LAUNCH_DEP((k_smooth9<false, false, true>), tile_grid(f.nz, f.nx), kSmThreads, kSm9Smem, s.stream, f.view9(),
                    (const double *)f.b, (const double *)f.r, f.x, nu, now, (const double *)nullptr, 0, 0,
                    (const PcgState *)st);
-        LAUNCH(k_residual9, grid_for(s, f.nz, f.nx, 8), kBlock, 0, s.stream, f.view9(), (const double *)f.b,
+        LAUNCH_DEP(k_residual9, grid_for(s, f.nz, f.nx, 8), kBlock, 0, s.stream, f.view9(), (const double *)f.b,
                (const double *)f.x, f.r, st);
-        LAUNCH(k_restrict, grid_for(s, c.nz, c.nx, 8), kBlock, 0, s.stream, f.w, (const double *)f.r, f.nz, f.nx,
+        LAUNCH_DEP(k_restrict, grid_for(s, c.nz, c.nx, 8), kBlock, 0, s.stream, f.w, (const double *)f.r, f.nz, f.nx,
                c.b, c.nz, c.nx, st);
         cycle(l + 1, true);
         if ((int)(l + 1) >= s.w_lo && (int)(l + 1) <= s.w_hi && l + 1 < nlev - 1) cycle(l + 1, false);
-        LAUNCH((k_smooth9<false, true, false>), tile_grid(f.nz, f.nx), kSmThreads, 0, s.stream, f.view9(),
+        LAUNCH_DEP((k_smooth9<false, true, false>), tile_grid(f.nz, f.nx), kSmThreads, kSm9SmemUp, s.stream, f.view9(),
                (const double *)f.b, (const double *)f.x, f.r, nu, f.w, (const double *)c.r, c.nz, c.nx,
                (const PcgState *)st);
     };
@@ -937,7 +1044,7 @@ void mg_vcycle(Solver &s, const double *r, double *ztmp, double *zout, PcgState 
     if (1 >= s.w_lo && 1 <= s.w_hi && nlev > 2) cycle(1, false);
     {
         Level &c = s.levels[1];
-        LAUNCH(k_up5, up_grid(s), kDnThreads, kUpSmem, s.stream, v5, r, (const double *)ztmp, zout, s.levels[0].w,
+        LAUNCH_DEP(k_up5, up_grid(s), kDnThreads, kUpSmem, s.stream, v5, r, (const double *)ztmp, zout, s.levels[0].w,
                (const double *)c.r, c.nz, c.nx, st, init, part + 4 * kMaxPartials, cnt + 1);
     }
 }

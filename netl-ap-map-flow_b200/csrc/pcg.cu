@@ -13,7 +13,13 @@
 
 namespace lcl {
 
-__device__ __forceinline__ bool stopped(const PcgState *st) { return st->converged | st->failed; }
+__device__ __forceinline__ bool stopped(const PcgState *st)
+{
+#ifndef LCL_CPU_SIM
+    cudaGridDependencySynchronize();   // LAUNCH_DEP: the predecessor's results are visible from here on
+#endif
+    return st->converged | st->failed;
+}
 
 // r = b (x0 = 0), x = 0
 __global__ void __launch_bounds__(kBlock)
@@ -202,11 +208,11 @@ int pcg_solve(Solver &s, const BoundaryValues &bv, double rel_tol, int max_iter,
         return 0;
     }
     auto enqueue_iteration = [&]() {
-        LAUNCH(k_spmv5, g0, kBlock, 0, s.stream, v5, (const double *)s.d, s.q, s.state, part, cnt);
-        LAUNCH(k_update, g1, 256, 0, s.stream, s.x, s.r, (const double *)s.d, (const double *)s.q, n, s.state,
+        LAUNCH_DEP(k_spmv5, g0, kBlock, 0, s.stream, v5, (const double *)s.d, s.q, s.state, part, cnt);
+        LAUNCH_DEP(k_update, g1, 256, 0, s.stream, s.x, s.r, (const double *)s.d, (const double *)s.q, n, s.state,
                part + 4 * kMaxPartials, cnt + 5);
         mg_vcycle(s, s.r, s.z, s.q, s.state, false);
-        LAUNCH(k_direction, g1, 256, 0, s.stream, s.d, (const double *)s.q, n, (const PcgState *)s.state, 0);
+        LAUNCH_DEP(k_direction, g1, 256, 0, s.stream, s.d, (const double *)s.q, n, (const PcgState *)s.state, 0);
     };
 #ifndef LCL_CPU_SIM
     // Every argument of the steady-state iteration is a pointer or size fixed for the solver's lifetime

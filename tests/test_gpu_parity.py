@@ -126,6 +126,16 @@ def test_ragged_multi_tile_maps_all_sides_vs_oracle(shape, side):
     check_against_oracle(synth_params(outlet_side=side), a, pmask=anchored_open_mask(a, 1e-4, vertical))
 
 
+@pytest.mark.parametrize("shape", [(3, 3000), (2500, 2), (5, 1500), (1, 4000)])
+@pytest.mark.parametrize("side", [TOP, LEFT])
+def test_thin_strip_maps_vs_oracle(shape, side):
+    """Strips a few cells wide: the hierarchy degenerates to 1 x n levels, the levels k_tail_cycle holds in
+    shared memory are long framed rows (the shapes its shared-memory budget is sized for)."""
+    nz, nx = shape
+    a = synth_aperture(nz, nx, seed=nz * 7 + nx, sigma_c=2)
+    check_against_oracle(synth_params(outlet_side=side), a)
+
+
 def test_invalid_inputs_fail_with_reference_messages():
     a = synth_aperture(8, 8, seed=1, sigma_c=0)
     with pytest.raises(lcl._lib.LclError, match="INVALID BOUNDARY"):

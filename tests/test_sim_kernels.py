@@ -80,6 +80,13 @@ def test_sim_tiny_and_degenerate_maps(sim, shape):
     check(sim, params(voxel_size=1e-5, avg_factor=1.0, viscosity=1e-3, inlet_pressure=1000.0), a)
 
 
+@pytest.mark.parametrize("shape", [(3, 1200), (900, 2), (1, 1500)])
+def test_sim_thin_strip_maps(sim, shape):
+    """1 x n tail levels: long framed rows in k_tail_cycle's shared memory."""
+    a = synth_aperture(shape[0], shape[1], seed=shape[0] * 7 + shape[1], sigma_c=2)
+    check(sim, params(voxel_size=1e-5, avg_factor=1.0, viscosity=1e-3, inlet_pressure=1000.0), a)
+
+
 def test_sim_synthetic_contact_map(sim):
     a = synth_aperture(64, 80, seed=5, contact=0.2, sigma_k=5)
     f, s, o, so = check(sim, params(voxel_size=1e-5, avg_factor=1.0, viscosity=1e-3, inlet_pressure=1000.0), a,

@@ -191,7 +191,7 @@ def _ref_worker(args):
     return time.time() - t0
 
 
-def run_reference(args):
+def run_reference(args, emit):
     """--impl reference: the reference's CPU algorithm (oracle port; gfortran is absent so oracle/_ref
     cannot exist) on all host cores, one independent map per core like BulkRun would schedule them."""
     rank = int(os.environ.get("RANK", "0"))
@@ -224,7 +224,7 @@ def run_reference(args):
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
                              "sample": "%d x (%dx%d) maps per step" % (cores, n, n)},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    emit(line)
 
 
 def main():
@@ -239,8 +239,19 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=448)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    # The contract is ONE JSON line on stdout: libraries that print there (NCCL's version banner under
+    # torchrun does) are sent to stderr until the line is ready.
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(obj):
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
+        print(json.dumps(obj), flush=True)
+
     if args.impl == "reference":
-        return run_reference(args)
+        return run_reference(args, emit)
 
     import numpy as np
     import torch
@@ -264,7 +275,9 @@ def main():
 
     n = args.size
     cells = n * n
-    a_dev = synth_map_torch(n, rank, dev, contact=args.contact)
+    # weak scaling = the same work on every GPU: every rank solves the map of seed 20240601 (maps of other
+    # seeds need 13-16 iterations at 8192^2, which would measure the maps, not the scaling: profiles/README.md)
+    a_dev = synth_map_torch(n, 0, dev, contact=args.contact)
     p = synth_params()
     solver = lcl.LclSolver(n, n, device=local)
     outs = {k: torch.empty((n, n), dtype=torch.float64, device=dev) for k in FIELDS}
@@ -377,14 +390,14 @@ def main():
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": "%dx%d synthetic log-normal aperture map (sigma_c=8 cells), %.0f%% zero-aperture "
                                    "contact cells (sigma=16), constant-pressure inlet/outlet (1000 -> 0 Pa, TOP), "
-                                   "one map per GPU" % (n, n, 100 * args.contact),
+                                   "one map per GPU (the same map, seed 20240601, on every rank)" % (n, n, 100 * args.contact),
                        "cells_per_gpu": cells, "rel_tol": 1e-10, "pcg_iterations": iters / args.steps,
                        "l2": "inputs larger than L2 (%.0f MB per field vs 126 MB)" % (8 * cells / 1e6),
                        "host_wall_ms_per_step": wall_ms / args.steps,
                        "setup_ms": last["setup_ms"], "solve_ms": last["solve_ms"],
                        "rel_residual": last["rel_residual"], "rel_residual_scaled": last["rel_residual_scaled"]},
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu}
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 

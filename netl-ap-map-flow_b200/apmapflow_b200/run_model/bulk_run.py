@@ -4,8 +4,8 @@ Same public surface as the reference (constructor :57-72, ``dry_run`` :74, ``sta
 ``generate_input_files`` :130, ``_combine_run_params`` :208, ``_initialize_run`` :236,
 ``_check_processes`` :262, ``_start_simulations`` :286).  The scheduling resource changes from CPU
 cores and host RAM to GPUs and device memory: ``num_CPUs`` bounds the number of simulations in flight,
-``sys_RAM`` is the device-memory budget in GB, and the new ``devices`` keyword lists the GPUs the
-cases are dealt to round-robin (independent cases, no collective)."""
+``sys_RAM`` is the memory budget in GB of EACH device, and the new ``devices`` keyword lists the GPUs: a
+case goes to the device with the most free budget that can hold it (independent cases, no collective)."""
 import string
 from collections import defaultdict
 from itertools import product
@@ -45,7 +45,8 @@ class BulkRun(dict):
 
     def start(self):
         """Runs every generated input file; like the reference it returns when the QUEUE is empty
-        (bulk_run.py:126), the last simulations may still be finishing."""
+        (bulk_run.py:126), the last simulations may still be finishing -- they run on non-daemon threads,
+        so a script that ends here still gets them completed (``wait()`` is an extra, not a requirement)."""
         logger.info("Beginning bulk run of simulations")
         self._initialize_run()
         processes, ram_in_use = [], []
@@ -103,17 +104,27 @@ class BulkRun(dict):
                     return
             sleep(retest_delay)
 
+    def _free_per_device(self, processes, RAM_in_use):
+        """Free budget of every device: ``avail_RAM`` is per GPU, a run occupies the device it was sent to."""
+        free = {d: self.avail_RAM for d in self.devices}
+        for proc, ram in zip(processes, RAM_in_use):
+            dev = getattr(proc, "device", self.devices[0])
+            free[dev] = free.get(dev, self.avail_RAM) - ram
+        return free
+
     def _start_simulations(self, processes, RAM_in_use, spawn_delay=5, **kwargs):
-        free = self.avail_RAM - sum(RAM_in_use)
         while len(processes) < self.num_CPUs:
+            free = self._free_per_device(processes, RAM_in_use)
+            # emptiest device first; ties go round-robin so equal cases still spread over the GPUs
+            order = sorted(range(len(self.devices)),
+                           key=lambda k: (-free[self.devices[k]], (k - self._next_device) % len(self.devices)))
+            device = self.devices[order[0]]
             for i, inp_file in enumerate(self.input_file_list):
-                if inp_file.RAM_req <= free:
+                if inp_file.RAM_req <= free[device]:
                     inp_file = self.input_file_list.pop(i)
-                    device = self.devices[self._next_device % len(self.devices)]
-                    self._next_device += 1
+                    self._next_device = order[0] + 1
                     processes.append(run_model(inp_file, device=device))
                     RAM_in_use.append(inp_file.RAM_req)
-                    free = self.avail_RAM - sum(RAM_in_use)
                     sleep(spawn_delay)
                     break
             else:

@@ -256,7 +256,10 @@ class LclProcess(object):
         self.start_time = time.time()
         self.end_time = None
         self._show = show_stdout
-        self._thread = threading.Thread(target=self._run, daemon=True)
+        # NOT a daemon thread: the reference's runs are child processes that outlive the caller
+        # (apm_bulk_run.py:81 returns right after start()); the interpreter joins this thread at exit, so a
+        # script that ends while simulations are in flight still gets their output files complete
+        self._thread = threading.Thread(target=self._run, daemon=False)
         self._thread.start()
 
     def _run(self):
@@ -338,6 +341,7 @@ def run_model(input_file_obj, synchronous=False, show_stdout=False, device=0):
         proc = Popen((exe, input_file_obj.outfile_name), stdout=out, stderr=out, universal_newlines=True, env=env)
         proc.input_file = input_file_obj
         proc.start_time = time.time()
+        proc.device = device
         comm = _AsyncCommunicate(proc)
         comm.start()
         if synchronous:

@@ -190,6 +190,7 @@ struct Solver {
     int w_lo = 1, w_hi = 0;                        // levels visited twice per cycle (empty range: V-cycle)
     bool have_solution = false;    // x holds the pressure of the last solve
     bool have_hierarchy = false;   // conductances and multigrid operators of the last solve are in place
+    bool ap_valid = false;         // ap holds the staged aperture map of the last solve (not flux scratch)
     bool down_configured = false;   // k_down5 opted in to >48 KB dynamic shared memory on this device
     apm_lcl_params last_params{};
     Fine5 view5() const { return Fine5{tx, tz, txl, tzb, nz, nx}; }

@@ -357,6 +357,7 @@ struct Run {
     // messages go to the caller's buffer (stdout of the reference) and, once open, to the log file
     std::string out;
     FILE *flog = nullptr;
+    bool open_io_failed = false;   // OPEN_IO gave up: every file it had created is removed again (IO_MODULE.F:219-226)
     void to_stdout(const std::string &s) { out += s; out += '\n'; }
     void message(const std::string &s)
     {
@@ -898,7 +899,7 @@ int run(Run &r, int device)
 
     std::ifstream in;
     std::streampos resume = 0;
-    if (!open_io(r, in, resume)) return 1;
+    if (!open_io(r, in, resume)) { r.open_io_failed = true; return 1; }
     in.clear();
     in.seekg(resume);
     if (!read_master(r, in)) return 1;
@@ -1250,8 +1251,7 @@ extern "C" APM_LCL_API int apm_lcl_run_file(const char *inp_path, int device, ch
         }
     }
     // a failed OPEN_IO removes what it created (IO_MODULE.F:219-226); later failures keep the files
-    const bool io_failed = rc != 0 && r.flog == nullptr;
-    r.close_all(io_failed);
+    r.close_all(r.open_io_failed);
     r.to_stdout(" ");
     r.to_stdout("     **** EXITING PROGRAM ****");
     if (log && log_cap) {

@@ -136,6 +136,21 @@ def test_thin_strip_maps_vs_oracle(shape, side):
     check_against_oracle(synth_params(outlet_side=side), a)
 
 
+@pytest.mark.parametrize("base", [1e5, 1e7, 1e9])
+def test_back_pressure_does_not_cost_flux_accuracy(base):
+    """Fluxes are pressure differences: a common offset of the two boundary pressures must leave them alone
+    (the solve runs on the unit drop and is shifted afterwards; round-1 advisor finding)."""
+    a = synth_aperture(300, 260, seed=3, sigma_c=6, contact=0.1, sigma_k=10)
+    f0, s0 = lcl.lcl_solve(synth_params(inlet_pressure=100.0, outlet_pressure=0.0), a)
+    f1, s1 = lcl.lcl_solve(synth_params(inlet_pressure=base + 100.0, outlet_pressure=base), a)
+    assert s1["converged"] == 1 and s1["iterations"] == s0["iterations"]
+    assert s1["flow"] == pytest.approx(s0["flow"], rel=1e-6)
+    floor = 4 * np.finfo(float).eps * base / 100.0        # rounding of the stored absolute pressures
+    for k in ("flow_x", "flow_z"):
+        assert np.abs(f1[k] - f0[k]).max() <= (1e-6 + floor) * np.abs(f0["flow_m"]).max()
+    assert np.abs((f1["pressure"] - base) - f0["pressure"]).max() <= (1e-6 + floor) * 100.0
+
+
 def test_invalid_inputs_fail_with_reference_messages():
     a = synth_aperture(8, 8, seed=1, sigma_c=0)
     with pytest.raises(lcl._lib.LclError, match="INVALID BOUNDARY"):

@@ -133,6 +133,23 @@ def test_missing_input_and_map_and_overwrite(tmp_path):
     assert os.path.exists(tmp_path / "pres.csv")
 
 
+def test_partially_failing_open_io_removes_what_it_created(tmp_path):
+    """IO_MODULE.F:219-226: when any output file cannot be opened, every file OPEN_IO did open is removed
+    again -- also when the log file itself opened fine.  Left behind, the empty files would make the next
+    run (after the user removed the one offender) fail on each of them in turn."""
+    lib = sim_lib.load()
+    (tmp_path / "pres.csv").write_text("keep me\n")
+    inp = small_inp(tmp_path, OK_BODY, "parallel-plate-01vox.txt").replace("OVERWRITE\n", "")
+    rc, out = run(lib, str(tmp_path), inp)
+    assert rc == 1 and "pres.csv ALREADY EXISTS" in out
+    left = sorted(f for f in os.listdir(tmp_path) if not f.endswith(".inp"))
+    assert left == ["pres.csv"], left
+    assert (tmp_path / "pres.csv").read_text() == "keep me\n"
+    os.remove(tmp_path / "pres.csv")
+    rc, out = run(lib, str(tmp_path), inp)
+    assert rc == 0, out
+
+
 def test_units_and_rate_bc_through_files(tmp_path):
     body = ("INLET-RATE: 1.0 MM^3/SEC\nOUTLET-PRESS: 1 KPA\nOUTLET-SIDE: RIGHT\nFLUID-DENSITY: 1 G/CM^3\n"
             "FLUID-VISCOSITY: 1.0 CP\nMAP AVERAGING FACTOR: 10\nVOXEL SIZE: 10 MICRONS\nLOW-MASK: 0.0001\n"

@@ -94,6 +94,25 @@ def test_sim_synthetic_contact_map(sim):
     assert so["zeros"] > 0
 
 
+@pytest.mark.parametrize("base", [1e5, 1e7, 1e9])
+def test_sim_back_pressure_does_not_cost_flux_accuracy(sim, base):
+    """A common pressure offset must not change the fluxes (they are pressure differences): the solve runs on
+    the unit drop and is shifted afterwards.  Solving for absolute pressures lost 1e-3 of the local fluxes at
+    1e7 + 100 -> 1e7 Pa while reporting convergence (round-1 advisor finding)."""
+    a = synth_aperture(96, 80, seed=3, sigma_c=4, contact=0.1, sigma_k=6)
+    kw = dict(voxel_size=1e-5, avg_factor=1.0, viscosity=1e-3)
+    f0, s0 = lcl.lcl_solve(params(inlet_pressure=100.0, outlet_pressure=0.0, **kw), a, lib=sim)
+    f1, s1 = lcl.lcl_solve(params(inlet_pressure=base + 100.0, outlet_pressure=base, **kw), a, lib=sim)
+    assert s1["converged"] == 1 and s1["iterations"] == s0["iterations"]
+    assert s1["flow"] == pytest.approx(s0["flow"], rel=1e-6)
+    # what is left is the rounding of the stored absolute pressures (eps * base per cell), which the
+    # reference's FRAC_FLOW sees as well: the bar is 1e-6 of the largest flux plus that floor
+    floor = 4 * np.finfo(float).eps * base / 100.0
+    for k in ("flow_x", "flow_z"):
+        assert np.abs(f1[k] - f0[k]).max() <= (1e-6 + floor) * np.abs(f0["flow_m"]).max()
+    assert np.abs((f1["pressure"] - base) - f0["pressure"]).max() <= (1e-6 + floor) * 100.0
+
+
 def test_sim_invalid_boundary_conditions_fail(sim):
     a = synth_aperture(8, 8, seed=1, sigma_c=0)
     with pytest.raises(lcl._lib.LclError):

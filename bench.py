@@ -9,8 +9,10 @@ config 3 (8192x8192 log-normal map, ~20 % zero-aperture contact cells), the conf
 is quoted on.  `value` is measured with the aperture already resident in HBM (device pointers in,
 device pointers out); `e2e` goes through the same C-ABI call with pinned HOST buffers, so the H2D
 copy of the map and the D2H copy of all seven output fields are inside the timed region.
-N>1 (torchrun, one rank per GPU): each rank solves its own map of the same size (independent
-maps, the bulk_run sharding of BASELINE config 5; weak scaling, no data-path collective).
+N>1 (torchrun, one rank per GPU): the SAME map is cut into N row strips, one per GPU (BASELINE configs
+3/4: strip decomposition, strong scaling); ghost rows and dot products cross the GPUs inside the solver's
+kernels (peer stores over NVLink), torch.distributed only carries the IPC handles and the timing.
+`--mode bulk` measures the other multi-GPU use instead: independent maps, one per GPU (config 5, weak).
 """
 import argparse
 import json
@@ -238,6 +240,8 @@ def main():
     ap.add_argument("--ref-size", type=int, default=384)
     ap.add_argument("--cpu-sample", type=int, default=448)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--mode", default="striped", choices=["striped", "bulk"],
+                    help="N>1: one map striped over the GPUs (strong scaling) or one independent map per GPU (weak)")
     args = ap.parse_args()
     # The contract is ONE JSON line on stdout: libraries that print there (NCCL's version banner under
     # torchrun does) are sent to stderr until the line is ready.
@@ -275,12 +279,22 @@ def main():
 
     n = args.size
     cells = n * n
-    # weak scaling = the same work on every GPU: every rank solves the map of seed 20240601 (maps of other
-    # seeds need 13-16 iterations at 8192^2, which would measure the maps, not the scaling: profiles/README.md)
+    striped = world > 1 and args.mode == "striped"
+    # every rank generates the map of seed 20240601 (input generation is not timed).  Striped: each rank keeps
+    # the rows it needs.  Bulk: the same map on every rank, so that per-GPU work is fixed (maps of other seeds
+    # need 13-16 iterations at 8192^2, which would measure the maps, not the scaling: profiles/README.md)
     a_dev = synth_map_torch(n, 0, dev, contact=args.contact)
     p = synth_params()
-    solver = lcl.LclSolver(n, n, device=local)
-    outs = {k: torch.empty((n, n), dtype=torch.float64, device=dev) for k in FIELDS}
+    if striped:
+        solver = lcl.StripedLclSolver(n, n, device=local)
+        a_dev = a_dev[solver.a_lo:solver.a_hi].clone()
+        rows = solver.z_hi - solver.z_lo
+        torch.cuda.empty_cache()
+    else:
+        solver = lcl.LclSolver(n, n, device=local)
+        rows = n
+    outs = {k: torch.empty((rows, n), dtype=torch.float64, device=dev) for k in FIELDS}
+    units = cells if striped else world * cells          # cells all ranks solve per step
 
     def step_device():
         fo = lcl.Fields()
@@ -321,12 +335,12 @@ def main():
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_step = float(t.item())
-    value = world * cells / (ms_step * 1e-3) / 1e6
+    value = units / (ms_step * 1e-3) / 1e6
     last = {k: getattr(sc, k) for k, _ in lcl.Scalars._fields_}
 
     # ---------------------------------------------------------------- end to end, host buffers
     a_host = a_dev.cpu().pin_memory()
-    host_out = {k: torch.empty((n, n), dtype=torch.float64).pin_memory() for k in FIELDS}
+    host_out = {k: torch.empty((rows, n), dtype=torch.float64).pin_memory() for k in FIELDS}
 
     def step_host():
         import ctypes as C
@@ -350,16 +364,28 @@ def main():
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_ms = float(t.item())
-    e2e = {"value": world * cells / (e2e_ms * 1e-3) / 1e6, "unit": UNIT, "ms_per_step": e2e_ms,
-           "h2d_bytes_per_step": 8 * cells, "d2h_bytes_per_step": 8 * cells * len(FIELDS)}
+    # bytes crossing PCIe per step, summed over the ranks (a strip copies its rows plus one either side in, its
+    # own rows of the seven fields out)
+    t = torch.tensor([8.0 * a_host.numel(), 8.0 * rows * n * len(FIELDS)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    e2e = {"value": units / (e2e_ms * 1e-3) / 1e6, "unit": UNIT, "ms_per_step": e2e_ms,
+           "h2d_bytes_per_step": int(t[0].item()), "d2h_bytes_per_step": int(t[1].item())}
 
-    if rank != 0:
+    def finish():
+        if striped:
+            solver.close()
         if world > 1:
             dist.destroy_process_group()
-        return
+
+    if rank != 0 and not striped:
+        return finish()
 
     # ---------------------------------------------------------------- roofline of the kernels
+    # (striped: every rank times the kernels of ITS strip -- they are collective, the dot products meet across
+    # the GPUs inside them -- and rank 0 reports its own)
     peak, peak_src = measured_peak()
+    own_cells = rows * n
     step_device()
     kern = {}
     # launches per PCG iteration of each fine-level kernel (+ the level-1 kernels of the V-cycle)
@@ -369,37 +395,41 @@ def main():
         ms, nbytes = solver.time_kernel(name, reps=20)
         step_device() if name != list(per_iter)[-1] else None
         kern[name] = {"ms": ms, "GBps": nbytes / ms / 1e6, "frac": nbytes / ms / 1e6 / peak,
-                      "bytes_per_cell": nbytes / cells, "launches_per_iter": per_iter[name]}
+                      "bytes_per_cell": nbytes / own_cells, "launches_per_iter": per_iter[name]}
     dom = max((k for k in kern if k != "vcycle"), key=lambda k: kern[k]["ms"] * kern[k]["launches_per_iter"])
+    if rank != 0:
+        return finish()
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")
-    if os.path.exists(tpath):
+    if os.path.exists(tpath) and world == 1:
         tj = json.load(open(tpath))
         if tj.get("size") == n and dom in tj["kernels"]:
             traffic = tj["kernels"][dom]["dram_read_bytes"] + tj["kernels"][dom]["dram_write_bytes"]
     roofline = {"bound": "hbm", "kernel": dom, "achieved": kern[dom]["GBps"], "peak": peak, "unit": "GB/s",
                 "frac": kern[dom]["frac"], "traffic": traffic,
-                "algorithmic_bytes": kern[dom]["bytes_per_cell"] * cells, "peak_source": peak_src, "kernels": kern}
+                "algorithmic_bytes": kern[dom]["bytes_per_cell"] * own_cells, "peak_source": peak_src, "kernels": kern}
 
     cpu = None
     if not args.no_cpu_baseline:
         cpu, _, _ = cpu_baseline(args.cpu_sample)
 
+    how = ("ONE map cut into %d row strips, one per GPU (ghost rows and dot products by peer stores over NVLink)" % world
+           if striped else "one map per GPU (the same map, seed 20240601, on every rank)")
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
+            "scaling": "strong" if striped else "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": "%dx%d synthetic log-normal aperture map (sigma_c=8 cells), %.0f%% zero-aperture "
-                                   "contact cells (sigma=16), constant-pressure inlet/outlet (1000 -> 0 Pa, TOP), "
-                                   "one map per GPU (the same map, seed 20240601, on every rank)" % (n, n, 100 * args.contact),
-                       "cells_per_gpu": cells, "rel_tol": 1e-10, "pcg_iterations": iters / args.steps,
+                                   "contact cells (sigma=16), constant-pressure inlet/outlet (1000 -> 0 Pa, TOP), %s"
+                                   % (n, n, 100 * args.contact, how),
+                       "cells_per_gpu": own_cells, "rel_tol": 1e-10, "pcg_iterations": iters / args.steps,
                        "l2": "inputs larger than L2 (%.0f MB per field vs 126 MB)" % (8 * cells / 1e6),
                        "host_wall_ms_per_step": wall_ms / args.steps,
                        "setup_ms": last["setup_ms"], "solve_ms": last["solve_ms"],
                        "rel_residual": last["rel_residual"], "rel_residual_scaled": last["rel_residual_scaled"]},
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu}
     emit(line)
-    if world > 1:
-        dist.destroy_process_group()
+    finish()
 
 
 if __name__ == "__main__":

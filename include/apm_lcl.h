@@ -113,6 +113,26 @@ APM_LCL_API int apm_lcl_solver_destroy(apm_lcl_solver *s);
 APM_LCL_API int apm_lcl_solver_solve(apm_lcl_solver *s, const apm_lcl_params *p, const double *aperture,
                          apm_lcl_fields *out, apm_lcl_scalars *sc);
 
+/* One map on several GPUs (new -- the reference is one serial process): the map is cut into row
+ * strips, one per rank / process / GPU of ONE node.  Rank k creates its solver with
+ * apm_lcl_solver_create_striped, which fills `handle` (apm_lcl_peer_handle_bytes() bytes: the CUDA IPC handle
+ * of the rank's device slab); the host gathers the handles of all ranks in rank order (torch.distributed
+ * all_gather, MPI, a file -- the library has no rendezvous of its own) and passes the `world` handles to
+ * apm_lcl_solver_connect.  From then on apm_lcl_solver_solve is collective: every rank calls it with the same
+ * parameters, passes the aperture rows [a_lo, a_hi) of the map (its own rows plus one either side, see
+ * apm_lcl_solver_rows) and receives the rows [z_lo, z_hi) of every output field; the scalars are the whole
+ * map's and identical on every rank.  Ghost rows and dot products cross the GPUs inside the kernels (peer stores over
+ * NVLink); no NCCL call is on the data path.  Before destroying the solvers every rank calls
+ * apm_lcl_solver_disconnect, and the host puts a barrier between that and apm_lcl_solver_destroy (a slab must
+ * not be freed while a peer still maps it).  Maps too small to be worth striping are solved whole by every
+ * rank (then z_lo = 0, z_hi = nz on all of them).  world <= 16. */
+APM_LCL_API int apm_lcl_peer_handle_bytes(void);
+APM_LCL_API int apm_lcl_solver_create_striped(apm_lcl_solver **out, int device, int nx, int nz, int rank, int world,
+                                              void *handle);
+APM_LCL_API int apm_lcl_solver_connect(apm_lcl_solver *s, const void *handles);
+APM_LCL_API int apm_lcl_solver_disconnect(apm_lcl_solver *s);
+APM_LCL_API int apm_lcl_solver_rows(apm_lcl_solver *s, int *z_lo, int *z_hi, int *a_lo, int *a_hi);
+
 /* One-shot convenience (create + solve + destroy) on `device`. */
 APM_LCL_API int apm_lcl_solve(const apm_lcl_params *p, const double *aperture, int nx, int nz, int device,
                   apm_lcl_fields *out, apm_lcl_scalars *sc);
@@ -145,9 +165,10 @@ APM_LCL_API int apm_lcl_conductance(const apm_lcl_params *p, const double *apert
 /* Access to the most recent solve's device-resident state (for roofline benches): returns
  * device pointers owned by the solver, valid until the next solve/destroy.  name: "pressure", "width",
  * "tx", "tz", "txl", "tzb"; "r" and "q" (scratch: time_kernel("vcycle") computes q = M^-1 r);
- * diagnostics of the multigrid hierarchy: "nlevels" (answer in *count),
- * "L<l>.nz", "L<l>.nx" (answer in *count), "L<l>.C|S|E|N|NE|NW" (stored 9-point operator of level
- * l >= 1) and "L<l>.hw|he|vs|vn|csw|cse|cnw|cne|th|tv|tc" (interpolation weights level l -> l+1). */
+ * diagnostics of the multigrid hierarchy: "nlevels", "gather_level" (first level every rank holds whole;
+ * answers in *count), "L<l>.nz", "L<l>.nx", "L<l>.zlo", "L<l>.zhi" (answer in *count), "L<l>.C|S|E|N|NE|NW"
+ * (stored 9-point operator of level l >= 1) and "L<l>.hw|he|vs|vn|csw|cse|cnw|cne|th|tv|tc" (interpolation
+ * weights level l -> l+1).  A striped solver returns the rows it owns. */
 APM_LCL_API int apm_lcl_solver_device_field(apm_lcl_solver *s, const char *name, double **ptr, size_t *count);
 
 /* Times ONE kernel of the solve on the solver's current state, `reps` back-to-back launches on the

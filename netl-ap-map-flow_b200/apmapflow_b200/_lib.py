@@ -76,6 +76,8 @@ EXPORTS = (
     "apm_lcl_solver_create", "apm_lcl_solver_destroy", "apm_lcl_solver_solve", "apm_lcl_solve",
     "apm_lcl_conductance", "apm_lcl_solver_device_field", "apm_lcl_solver_time_kernel",
     "apm_lcl_run_file", "apm_lcl_bulk_solve",
+    "apm_lcl_peer_handle_bytes", "apm_lcl_solver_create_striped", "apm_lcl_solver_connect",
+    "apm_lcl_solver_disconnect", "apm_lcl_solver_rows",
 )
 
 _lib = None
@@ -104,6 +106,12 @@ def bind(lib):
     lib.apm_lcl_default_params.restype = None
     lib.apm_lcl_solver_create.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int]
     lib.apm_lcl_solver_destroy.argtypes = [C.c_void_p]
+    lib.apm_lcl_peer_handle_bytes.restype = C.c_int
+    lib.apm_lcl_solver_create_striped.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                                  C.c_void_p]
+    lib.apm_lcl_solver_connect.argtypes = [C.c_void_p, C.c_void_p]
+    lib.apm_lcl_solver_disconnect.argtypes = [C.c_void_p]
+    lib.apm_lcl_solver_rows.argtypes = [C.c_void_p] + [C.POINTER(C.c_int)] * 4
     lib.apm_lcl_solver_solve.argtypes = [C.c_void_p, C.POINTER(Params), C.c_void_p,
                                          C.POINTER(Fields), C.POINTER(Scalars)]
     lib.apm_lcl_solve.argtypes = [C.POINTER(Params), C.c_void_p, C.c_int, C.c_int, C.c_int,

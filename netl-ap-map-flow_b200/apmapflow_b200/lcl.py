@@ -81,6 +81,201 @@ class LclSolver(object):
         return ms.value, nbytes.value
 
 
+class StripedLclSolver(object):
+    """One map cut into row strips over the ranks of a ``torch.distributed`` group, one process and one GPU
+    per rank on ONE node (apm_lcl_solver_create_striped / _connect).  torch.distributed only
+    carries the peer handles at start-up and the barrier at shut-down: ghost rows and dot products move
+    between the GPUs inside the solver's kernels.  ``solve`` is collective."""
+
+    def __init__(self, nx, nz, device=0, group=None, lib=None):
+        import torch.distributed as dist
+        self.lib = lib if lib is not None else _lib.load()
+        self.group = group
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        self.nx, self.nz, self.device = int(nx), int(nz), int(device)
+        nbytes = int(self.lib.apm_lcl_peer_handle_bytes())
+        handle = C.create_string_buffer(nbytes)
+        self._h = C.c_void_p()
+        rc = self.lib.apm_lcl_solver_create_striped(C.byref(self._h), self.device, self.nx, self.nz, self.rank,
+                                                    self.world, handle)
+        # every rank reports, so that a failure on one does not leave the others waiting in the gather
+        status = [None] * self.world
+        dist.all_gather_object(status, (rc, handle.raw, self._error()), group=group)
+        bad = [(k, st[2]) for k, st in enumerate(status) if st[0] != 0]
+        if bad:
+            self.close(barrier=False)
+            raise _lib.LclError("striped solver: rank %d: %s" % bad[0])
+        blob = b"".join(st[1] for st in status)
+        rc = self.lib.apm_lcl_solver_connect(self._h, blob)
+        status = [None] * self.world
+        dist.all_gather_object(status, (rc, self._error()), group=group)
+        bad = [(k, st[1]) for k, st in enumerate(status) if st[0] != 0]
+        if bad:
+            self.close(barrier=False)
+            raise _lib.LclError("striped solver: rank %d could not map its peers: %s" % bad[0])
+        z = [C.c_int() for _ in range(4)]
+        self.lib.apm_lcl_solver_rows(self._h, *[C.byref(v) for v in z])
+        self.z_lo, self.z_hi, self.a_lo, self.a_hi = [v.value for v in z]
+
+    def _error(self):
+        return (self.lib.apm_lcl_last_error() or b"").decode("utf-8", "replace")
+
+    def close(self, barrier=True):
+        """Collective: unmap the peers, wait for everyone, free the slab (a slab must outlive its mappings)."""
+        if getattr(self, "_h", None):
+            self.lib.apm_lcl_solver_disconnect(self._h)
+            if barrier:
+                import torch.distributed as dist
+                dist.barrier(group=self.group)
+            self.lib.apm_lcl_solver_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close(barrier=exc[0] is None)
+
+    def solve(self, params, aperture, fields=FIELD_NAMES):
+        """``aperture`` is the whole map [nz, nx] (the rank's rows are taken from it) or just the rows
+        [a_lo, a_hi) this rank needs; numpy in -> numpy out, CUDA tensor in -> CUDA tensors out.  Returns
+        (dict name -> array of the rows [z_lo, z_hi) this rank owns, dict of whole-map scalars)."""
+        rows_in, rows_out = self.a_hi - self.a_lo, self.z_hi - self.z_lo
+        if aperture.shape[0] == self.nz and rows_in != self.nz:
+            aperture = aperture[self.a_lo:self.a_hi]
+        assert tuple(aperture.shape) == (rows_in, self.nx), (tuple(aperture.shape), rows_in, self.nx)
+        out = Fields()
+        arrays = {}
+        if _is_torch_cuda(aperture):
+            import torch
+            a = aperture.to(torch.float64).contiguous()
+            ptr = a.data_ptr()
+            for name in fields:
+                arrays[name] = torch.empty((rows_out, self.nx), dtype=torch.float64, device=a.device)
+                setattr(out, name, arrays[name].data_ptr())
+            torch.cuda.current_stream(a.device).synchronize()
+        else:
+            a = np.ascontiguousarray(aperture, dtype=np.float64)
+            ptr = a.ctypes.data
+            for name in fields:
+                arrays[name] = np.empty((rows_out, self.nx))
+                setattr(out, name, arrays[name].ctypes.data)
+        sc = Scalars()
+        rc = self.lib.apm_lcl_solver_solve(self._h, C.byref(params), ptr, C.byref(out), C.byref(sc))
+        d = sc.as_dict()
+        d["gpu_launches"] = int(self.lib.apm_lcl_last_launch_count())
+        if rc != 0:
+            err = _lib.LclError("rank %d: %s" % (self.rank, self._error()))
+            err.scalars = d
+            err.fields = arrays
+            raise err
+        return arrays, d
+
+    def time_kernel(self, name, reps=20):
+        """Collective: every rank times the kernel on its own strip (the dot products inside still meet)."""
+        return LclSolver.time_kernel(self, name, reps)
+
+    def gather(self, arrays):
+        """Whole-map host arrays on every rank from the per-rank strips (convenience for tests and writers)."""
+        import torch.distributed as dist
+        host = {k: (v.cpu().numpy() if _is_torch_cuda(v) else v) for k, v in arrays.items()}
+        parts = [None] * self.world
+        dist.all_gather_object(parts, (self.z_lo, self.z_hi, host), group=self.group)
+        if self.z_hi - self.z_lo == self.nz:          # nothing was striped: every rank holds the whole map
+            return host
+        return {k: np.concatenate([p[2][k] for p in sorted(parts, key=lambda p: p[0])], axis=0) for k in host}
+
+
+class StripedGroup(object):
+    """One map cut into row strips over several GPUs driven by ONE process: a solver per device, a host
+    thread per solver (ctypes drops the GIL), the peers addressed directly instead of through CUDA IPC.
+    ``devices`` may name a GPU more than once (strips then share it: a way to run the striped path on a
+    single-GPU box)."""
+
+    def __init__(self, nx, nz, devices, lib=None):
+        self.lib = lib if lib is not None else _lib.load()
+        self.nx, self.nz, self.devices = int(nx), int(nz), [int(d) for d in devices]
+        world = len(self.devices)
+        nbytes = int(self.lib.apm_lcl_peer_handle_bytes())
+        self._h, blobs = [], []
+        try:
+            for rank, dev in enumerate(self.devices):
+                h, blob = C.c_void_p(), C.create_string_buffer(nbytes)
+                _lib_check(self.lib, self.lib.apm_lcl_solver_create_striped(C.byref(h), dev, self.nx, self.nz, rank, world, blob))
+                self._h.append(h)
+                blobs.append(blob.raw)
+            for h in self._h:
+                _lib_check(self.lib, self.lib.apm_lcl_solver_connect(h, b"".join(blobs)))
+        except Exception:
+            self.close()
+            raise
+        self.rows = []
+        for h in self._h:
+            z = [C.c_int() for _ in range(4)]
+            self.lib.apm_lcl_solver_rows(h, *[C.byref(v) for v in z])
+            self.rows.append(tuple(v.value for v in z))
+
+    def close(self):
+        for h in self._h:
+            self.lib.apm_lcl_solver_disconnect(h)
+        for h in self._h:
+            self.lib.apm_lcl_solver_destroy(h)
+        self._h = []
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def solve(self, params, aperture, fields=FIELD_NAMES):
+        """``aperture``: whole map [nz, nx], host numpy array.  Returns (dict of whole-map arrays, scalars)."""
+        import threading
+        a = np.ascontiguousarray(aperture, dtype=np.float64)
+        assert a.shape == (self.nz, self.nx)
+        whole = {name: np.empty((self.nz, self.nx)) for name in fields}
+        results = [None] * len(self._h)
+
+        def work(k):
+            z_lo, z_hi, a_lo, a_hi = self.rows[k]
+            out = Fields()
+            for name in fields:
+                setattr(out, name, whole[name][z_lo:z_hi].ctypes.data)     # row slices of a C array are contiguous
+            sc = Scalars()
+            rc = self.lib.apm_lcl_solver_solve(self._h[k], C.byref(params), a[a_lo:a_hi].ctypes.data, C.byref(out), C.byref(sc))
+            d = sc.as_dict()
+            d["gpu_launches"] = int(self.lib.apm_lcl_last_launch_count())
+            results[k] = (rc, d, (self.lib.apm_lcl_last_error() or b"").decode("utf-8", "replace"))
+
+        threads = [threading.Thread(target=work, args=(k,)) for k in range(len(self._h))]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join()
+        bad = [(k, r[2]) for k, r in enumerate(results) if r[0] != 0]
+        if bad:
+            err = _lib.LclError("striped solve: rank %d: %s" % bad[0])
+            err.scalars = [r[1] for r in results]
+            err.fields = whole
+            raise err
+        d = dict(results[0][1])
+        d["gpu_launches"] = sum(r[1]["gpu_launches"] for r in results)
+        d["per_rank"] = [r[1] for r in results]
+        return whole, d
+
+
+def _lib_check(lib, rc):
+    if rc != 0:
+        raise _lib.LclError((lib.apm_lcl_last_error() or b"").decode("utf-8", "replace"))
+
+
+def lcl_solve_striped(params, aperture, devices, fields=FIELD_NAMES, lib=None):
+    """One-shot solve of one map striped over ``devices`` from a single process."""
+    nz, nx = aperture.shape
+    with StripedGroup(nx, nz, devices, lib=lib) as g:
+        return g.solve(params, aperture, fields=fields)
+
+
 def lcl_solve(params, aperture, device=0, fields=FIELD_NAMES, lib=None):
     """One-shot solve of a single map."""
     nz, nx = aperture.shape

@@ -10,7 +10,7 @@
 #include <thread>
 #include <limits>
 
-#include "common.cuh"
+#include "dist.cuh"
 
 namespace lcl {
 
@@ -33,18 +33,13 @@ static bool is_device_ptr(const void *p)
     return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
 }
 
-static void alloc_d(double **p, size_t count) { CUDA_CHECK(cudaMalloc((void **)p, (count ? count : 1) * sizeof(double))); }
-
 static void solver_free(Solver *s)
 {
     if (!s) return;
     cudaSetDevice(s->device);
-    mg_free(*s);
-    double *ptrs[] = {s->ap, s->width, s->tx, s->tz, s->txl, s->tzb, s->x, s->r, s->d, s->q, s->z, s->red, s->scal};
-    for (double *p : ptrs)
-        if (p) cudaFree(p);
-    if (s->red_counters) cudaFree(s->red_counters);
-    if (s->state) cudaFree(s->state);
+    if (s->stream) cudaStreamSynchronize(s->stream);
+    if (s->connected) slab_disconnect(*s);
+    slab_destroy(*s);
     if (s->state_host) cudaFreeHost(s->state_host);
     if (s->scal_host) cudaFreeHost(s->scal_host);
     for (auto &e : s->ev)
@@ -57,7 +52,27 @@ static void solver_free(Solver *s)
     delete s;
 }
 
-static Solver *solver_new(int device, int nx, int nz)
+// Every device array of the solver, taken from one slab in a fixed order (the same on every rank: an
+// object's offset is what locates it in a peer's slab).  Runs twice: counting pass, then for real.
+static void layout(Solver &s, Arena &a)
+{
+    // peer window first (its address IS the slab address), the local bookkeeping right behind it
+    a.take_bytes(sizeof(PeerWindow));
+    s.dist.local = (DistLocal *)a.take_bytes(sizeof(DistLocal));
+    const Level &L0 = s.levels[0];
+    auto rows = [&](int pitch) { return a.take_rows(pitch, s.nz, L0.striped, L0.cut, s.rank, s.world); };
+    double **fields[] = {&s.ap, &s.width, &s.tx, &s.tz, &s.x, &s.r, &s.d, &s.q, &s.z};
+    for (auto f : fields) *f = rows(s.nx);
+    s.txl = rows(1);
+    s.tzb = a.take(s.nx);
+    s.red = a.take((size_t)32 * kMaxPartials);
+    s.scal = a.take(64);
+    s.red_counters = (unsigned int *)a.take_bytes(16 * sizeof(unsigned int));
+    s.state = (PcgState *)a.take_bytes(sizeof(PcgState));
+    mg_allocate(s, a);
+}
+
+static Solver *solver_new(int device, int nx, int nz, int rank, int world, void *handle_out)
 {
     int count = 0;
     if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) {
@@ -66,28 +81,29 @@ static Solver *solver_new(int device, int nx, int nz)
     }
     if (device < 0 || device >= count) throw CudaError{"invalid CUDA device index"};
     if (nx < 1 || nz < 1) throw CudaError{"map dimensions must be >= 1"};
+    if (world < 1 || world > kMaxRanks || rank < 0 || rank >= world) throw CudaError{"invalid rank / world size"};
+    if (world > 1 && !handle_out) throw CudaError{"a striped solver needs a buffer for its peer handle"};
     CUDA_CHECK(cudaSetDevice(device));
     Solver *s = new Solver();
     try {
         s->device = device; s->nx = nx; s->nz = nz; s->n = (size_t)nx * nz;
+        s->rank = rank; s->world = world;
         cudaDeviceProp prop{};
         CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
         s->num_sms = prop.multiProcessorCount;
         CUDA_CHECK(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
         CUDA_CHECK(cudaStreamCreateWithFlags(&s->copy_stream, cudaStreamNonBlocking));
-        double **fields[] = {&s->ap, &s->width, &s->tx, &s->tz, &s->x, &s->r, &s->d, &s->q, &s->z};
-        for (auto f : fields) alloc_d(f, s->n);
-        alloc_d(&s->txl, nz);
-        alloc_d(&s->tzb, nx);
-        alloc_d(&s->red, (size_t)32 * kMaxPartials);
-        alloc_d(&s->scal, 64);
-        CUDA_CHECK(cudaMalloc((void **)&s->red_counters, 16 * sizeof(unsigned int)));
-        CUDA_CHECK(cudaMemset(s->red_counters, 0, 16 * sizeof(unsigned int)));
-        CUDA_CHECK(cudaMalloc((void **)&s->state, sizeof(PcgState)));
+        mg_plan(*s);
+        Arena count_pass;
+        layout(*s, count_pass);
+        slab_create(*s, count_pass.used + 256, handle_out);
+        Arena real;
+        real.base = s->slab;
+        layout(*s, real);
         CUDA_CHECK(cudaMallocHost((void **)&s->state_host, sizeof(PcgState)));
         CUDA_CHECK(cudaMallocHost((void **)&s->scal_host, 64 * sizeof(double)));
         for (auto &e : s->ev) CUDA_CHECK(cudaEventCreate(&e));
-        mg_allocate(*s);
+        if (world == 1) slab_connect(*s, nullptr);   // a single rank is connected to itself
         if (const char *e = getenv("APM_LCL_NU_L1")) s->nu_coarse = atoi(e);     // tuning knobs
         if (const char *e = getenv("APM_LCL_NU_DEEP")) s->nu_deep = atoi(e);
         s->tail.nu = s->tail_top == 1 ? s->nu_coarse : s->nu_deep;
@@ -110,14 +126,17 @@ static Solver *solver_new(int device, int nx, int nz)
     return s;
 }
 
-// sum over one side's boundary faces of T_b (P_b - p_i): the flow entering through that side
-__global__ void k_side_inflow(Fine5 v, const double *__restrict__ p, int side, double pb, double *out)
+// sum over one side's boundary faces of T_b (P_b - p_i): the flow entering through that side (a strip adds
+// up the faces of its own rows; the ranks' shares meet in rank order)
+__global__ void k_side_inflow(Fine5 v, const double *__restrict__ p, int side, double pb, double *out, Dist dc)
 {
     __shared__ double sh[256];
     const int nz = v.nz, nx = v.nx;
-    const int count = (side == APM_LCL_LEFT || side == APM_LCL_RIGHT) ? nz : nx;
+    const bool rows = side == APM_LCL_LEFT || side == APM_LCL_RIGHT;
+    const int k0 = rows ? v.zlo : 0, k1 = rows ? v.zhi : nx;
+    const bool mine = rows || (side == APM_LCL_BOTTOM ? v.zlo == 0 : v.zhi == nz);
     double acc = 0.0;
-    for (int k = threadIdx.x; k < count; k += blockDim.x) {
+    for (int k = k0 + threadIdx.x; mine && k < k1; k += blockDim.x) {
         double t, pi;
         if (side == APM_LCL_LEFT) { t = v.txl[k]; pi = p[(size_t)k * nx]; }
         else if (side == APM_LCL_RIGHT) { t = v.tx[(size_t)k * nx + nx - 1]; pi = p[(size_t)k * nx + nx - 1]; }
@@ -131,12 +150,11 @@ __global__ void k_side_inflow(Fine5 v, const double *__restrict__ p, int side, d
         if ((int)threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
         __syncthreads();
     }
-    if (threadIdx.x == 0) *out = sh[0];
-}
-
-__global__ void k_fill(double *x, size_t n, double v)
-{
-    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) x[i] = v;
+    if (threadIdx.x == 0) {
+        double tot[1] = {sh[0]};
+        dist_sum<1>(dc, tot);
+        *out = tot[0];
+    }
 }
 
 static int opposite(int side)
@@ -160,10 +178,12 @@ static BoundaryValues halo_values(int outlet_side, double inl, double out)
     return bv;
 }
 
-static void copy_out(Solver &s, double *dst, const double *src_dev, size_t count)
+// results leave as the rows this rank owns: src_dev is a fine-level array (virtual base, global row numbers)
+static void copy_out(Solver &s, double *dst, const double *src_dev)
 {
-    if (!dst || dst == src_dev) return;
-    CUDA_CHECK(cudaMemcpyAsync(dst, src_dev, count * sizeof(double),
+    const double *src = src_dev + (size_t)s.zlo * s.nx;
+    if (!dst || dst == src) return;
+    CUDA_CHECK(cudaMemcpyAsync(dst, src, s.own_cells() * sizeof(double),
                                is_device_ptr(dst) ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, s.stream));
 }
 
@@ -174,11 +194,17 @@ static void validate(const apm_lcl_params &p)
     if (!(p.voxel_size > 0) || !(p.avg_factor > 0)) throw CudaError{"voxel size and averaging factor must be > 0"};
 }
 
+// aperture rows a rank passes in: its own plus one either side (the corner points average across the cut)
+static int ap_lo(const Solver &s) { return s.zlo > 0 ? s.zlo - 1 : 0; }
+static int ap_hi(const Solver &s) { return s.zhi < s.nz ? s.zhi + 1 : s.nz; }
+
+// returns the aperture as a fine-level array (global row numbers): the caller's device memory, or the staged copy
 static const double *stage_aperture(Solver &s, const double *aperture)
 {
     if (!aperture) throw CudaError{"aperture pointer is NULL"};
-    if (is_device_ptr(aperture)) return aperture;
-    CUDA_CHECK(cudaMemcpyAsync(s.ap, aperture, s.n * sizeof(double), cudaMemcpyHostToDevice, s.stream));
+    const size_t off = (size_t)ap_lo(s) * s.nx, cnt = (size_t)(ap_hi(s) - ap_lo(s)) * s.nx;
+    if (is_device_ptr(aperture)) return aperture - off;
+    CUDA_CHECK(cudaMemcpyAsync(s.ap + off, aperture, cnt * sizeof(double), cudaMemcpyHostToDevice, s.stream));
     return s.ap;
 }
 
@@ -199,6 +225,7 @@ static void read_map_scalars(Solver &s, const apm_lcl_params &p, apm_lcl_scalars
 static void do_solve(Solver &s, const apm_lcl_params &p, const double *aperture, apm_lcl_fields *out, apm_lcl_scalars *sc)
 {
     validate(p);
+    if (!s.connected) throw CudaError{"striped solver is not connected to its peers (apm_lcl_solver_connect)"};
     CUDA_CHECK(cudaSetDevice(s.device));
     g_launches = 0;
     const double rel_tol = p.rel_tol > 0 ? p.rel_tol : 1e-10;
@@ -206,6 +233,7 @@ static void do_solve(Solver &s, const apm_lcl_params &p, const double *aperture,
     apm_lcl_scalars local{};
     if (!sc) sc = &local;
     std::memset(sc, 0, sizeof(*sc));
+    const size_t own_off = (size_t)s.zlo * s.nx;
 
     const double *ap_dev = stage_aperture(s, aperture);
     CUDA_CHECK(cudaEventRecord(s.ev[0], s.stream));
@@ -220,7 +248,8 @@ static void do_solve(Solver &s, const apm_lcl_params &p, const double *aperture,
     if (out && out->aperture && !is_device_ptr(out->aperture)) {
         CUDA_CHECK(cudaEventRecord(s.ev[5], s.stream));
         CUDA_CHECK(cudaStreamWaitEvent(s.copy_stream, s.ev[5], 0));
-        CUDA_CHECK(cudaMemcpyAsync(out->aperture, s.width, s.n * sizeof(double), cudaMemcpyDeviceToHost, s.copy_stream));
+        CUDA_CHECK(cudaMemcpyAsync(out->aperture, s.width + own_off, s.own_cells() * sizeof(double), cudaMemcpyDeviceToHost,
+                                   s.copy_stream));
         early.active = true;
     }
     mg_setup(s);
@@ -239,7 +268,7 @@ static void do_solve(Solver &s, const apm_lcl_params &p, const double *aperture,
         // pressures -- lose accuracy with any back pressure (1e7 + 100 -> 1e7 Pa: 1e-3 local flux error while
         // "converged"); the reference's direct solve has no such dependence.
         rc_iters = pcg_solve(s, halo_values(side, 1.0, 0.0), rel_tol, max_iter, sc);
-        if (rc_iters >= 0) launch_affine(s, s.x, s.n, inl - outp, outp);
+        if (rc_iters >= 0) launch_affine(s, s.own(s.x), s.own_cells(), inl - outp, outp);
     } else if ((has_out && !has_in && rate_in && !rate_out) || (has_in && !has_out && rate_out && !rate_in)) {
         // Group-node (flow rate) BC, D4_SOLVER_MODULE.F:263-328, by linearity: the group side is an
         // equipotential, so solve once with it at P0+1 and the pressure side at P0 (here P0 := 0),
@@ -249,14 +278,14 @@ static void do_solve(Solver &s, const apm_lcl_params &p, const double *aperture,
         BoundaryValues bv = inlet_group ? halo_values(side, 1.0, 0.0) : halo_values(side, 0.0, 1.0);
         rc_iters = pcg_solve(s, bv, rel_tol, max_iter, sc);
         if (rc_iters >= 0) {
-            LAUNCH(k_side_inflow, 1, 256, 0, s.stream, s.view5(), (const double *)s.x, gside, 1.0, s.scal + 20);
+            LAUNCH(k_side_inflow, 1, 256, 0, s.stream, s.view5(), (const double *)s.x, gside, 1.0, s.scal + 20, s.dist);
             CUDA_CHECK(cudaMemcpyAsync(s.scal_host + 20, s.scal + 20, sizeof(double), cudaMemcpyDeviceToHost, s.stream));
             CUDA_CHECK(cudaStreamSynchronize(s.stream));
             const double K = s.scal_host[20];
             const double p0 = inlet_group ? outp : inl;
             const double rate = inlet_group ? p.inlet_rate : -p.outlet_rate;
             const double scale = rate / K;
-            launch_affine(s, s.x, s.n, scale, p0);
+            launch_affine(s, s.own(s.x), s.own_cells(), scale, p0);
             if (inlet_group) inl = p0 + scale; else outp = p0 + scale;   // APERTURE_MAP_FLOW.F:680-688
         }
     } else {
@@ -268,7 +297,12 @@ static void do_solve(Solver &s, const apm_lcl_params &p, const double *aperture,
     if (rc_iters < 0) throw CudaError{g_last_error};
     CUDA_CHECK(cudaEventRecord(s.ev[2], s.stream));
 
-    // fluxes + derived fields
+    // fluxes + derived fields (a strip reads one row of pressures beyond its own either side)
+    if (s.levels[0].striped) {
+        HaloSet hs;
+        hs.add(s.x);
+        halo_exchange(s, hs, s.nx, s.levels[0].cut, 1, 1, nullptr);
+    }
     apm_lcl_fields none{};
     if (!out) out = &none;
     const BoundaryValues bvf = halo_values(side, inl, outp);
@@ -276,15 +310,16 @@ static void do_solve(Solver &s, const apm_lcl_params &p, const double *aperture,
     double *scratch[5] = {s.r, s.d, s.q, s.z, s.ap};
     double *user[5] = {out->flow_x, out->flow_z, out->flow_m, out->reynolds, out->residual};
     double **slot[5] = {&fo.qx, &fo.qz, &fo.qm, &fo.ren, &fo.res};
+    // the kernel indexes by global cell number: a caller's device buffer starts at the rank's first own row
     for (int k = 0; k < 5; k++)
-        *slot[k] = user[k] ? (is_device_ptr(user[k]) ? user[k] : scratch[k]) : nullptr;
+        *slot[k] = user[k] ? (is_device_ptr(user[k]) ? user[k] - own_off : scratch[k]) : nullptr;
     // s.ap doubles as the residual scratch: the staged copy of the map is dead after the conductance pass
     s.ap_valid = ap_dev == s.ap && fo.res != s.ap;
     launch_flux(s, p, s.x, bvf, fo);
     CUDA_CHECK(cudaEventRecord(s.ev[3], s.stream));
-    for (int k = 0; k < 5; k++) copy_out(s, user[k], *slot[k], s.n);
-    copy_out(s, out->pressure, s.x, s.n);
-    if (!early.active) copy_out(s, out->aperture, s.width, s.n);
+    for (int k = 0; k < 5; k++) copy_out(s, user[k], *slot[k]);
+    copy_out(s, out->pressure, s.x);
+    if (!early.active) copy_out(s, out->aperture, s.width);
     CUDA_CHECK(cudaEventRecord(s.ev[4], s.stream));
     read_map_scalars(s, p, sc);   // synchronises the stream
 
@@ -354,9 +389,64 @@ int apm_lcl_solver_create(apm_lcl_solver **out, int device, int nx, int nz)
     API_TRY
     if (!out) throw CudaError{"out pointer is NULL"};
     *out = nullptr;
-    Solver *s = solver_new(device, nx, nz);
+    Solver *s = solver_new(device, nx, nz, 0, 1, nullptr);
     *out = new apm_lcl_solver{s};
     g_last_error.clear();
+    return 0;
+    API_CATCH
+}
+
+int apm_lcl_peer_handle_bytes(void) { return kPeerHandleBytes; }
+
+int apm_lcl_solver_create_striped(apm_lcl_solver **out, int device, int nx, int nz, int rank, int world, void *handle)
+{
+    API_TRY
+    if (!out) throw CudaError{"out pointer is NULL"};
+    *out = nullptr;
+    Solver *s = solver_new(device, nx, nz, rank, world, handle);
+    *out = new apm_lcl_solver{s};
+    g_last_error.clear();
+    return 0;
+    API_CATCH
+}
+
+int apm_lcl_solver_connect(apm_lcl_solver *h, const void *handles)
+{
+    API_TRY
+    if (!h || !h->s) throw CudaError{"solver pointer is NULL"};
+    Solver &s = *h->s;
+    CUDA_CHECK(cudaSetDevice(s.device));
+    if (s.connected) slab_disconnect(s);
+    slab_connect(s, handles);
+    // nothing is striped (map too small to be worth it): every rank solves the whole map and no kernel
+    // combines anything across ranks
+    if (s.gather_level == 0) s.dist.world = 1;
+    g_last_error.clear();
+    return 0;
+    API_CATCH
+}
+
+int apm_lcl_solver_disconnect(apm_lcl_solver *h)
+{
+    API_TRY
+    if (!h || !h->s) throw CudaError{"solver pointer is NULL"};
+    Solver &s = *h->s;
+    CUDA_CHECK(cudaSetDevice(s.device));
+    CUDA_CHECK(cudaStreamSynchronize(s.stream));
+    if (s.connected) slab_disconnect(s);
+    return 0;
+    API_CATCH
+}
+
+int apm_lcl_solver_rows(apm_lcl_solver *h, int *z_lo, int *z_hi, int *a_lo, int *a_hi)
+{
+    API_TRY
+    if (!h || !h->s) throw CudaError{"solver pointer is NULL"};
+    const Solver &s = *h->s;
+    if (z_lo) *z_lo = s.zlo;
+    if (z_hi) *z_hi = s.zhi;
+    if (a_lo) *a_lo = ap_lo(s);
+    if (a_hi) *a_hi = ap_hi(s);
     return 0;
     API_CATCH
 }
@@ -460,7 +550,7 @@ int apm_lcl_conductance(const apm_lcl_params *p, const double *aperture, int nx,
     API_TRY
     if (!p) throw CudaError{"params pointer is NULL"};
     validate(*p);
-    s = solver_new(device, nx, nz);
+    s = solver_new(device, nx, nz, 0, 1, nullptr);
     g_launches = 0;
     const double *ap_dev = stage_aperture(*s, aperture);
     launch_conductance(*s, *p, ap_dev);
@@ -469,12 +559,17 @@ int apm_lcl_conductance(const apm_lcl_params *p, const double *aperture, int nx,
     std::memset(sc, 0, sizeof(*sc));
     double *dtrx = nullptr, *dtrz = nullptr;
     const size_t ntrx = (size_t)nz * (nx + 1), ntrz = (size_t)(nz + 1) * nx;
+    auto alloc_d = [](double **p, size_t count) { CUDA_CHECK(cudaMalloc((void **)p, (count ? count : 1) * sizeof(double))); };
+    auto copy_n = [&](double *dst, const double *src, size_t count) {
+        CUDA_CHECK(cudaMemcpyAsync(dst, src, count * sizeof(double),
+                                   is_device_ptr(dst) ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, s->stream));
+    };
     if (trx) dtrx = is_device_ptr(trx) ? trx : (alloc_d(&dtrx, ntrx), dtrx);
     if (trz) dtrz = is_device_ptr(trz) ? trz : (alloc_d(&dtrz, ntrz), dtrz);
     if (trx || trz) export_reference_layout(*s, dtrx, dtrz);
-    copy_out(*s, width, s->width, s->n);
-    if (trx && dtrx != trx) copy_out(*s, trx, dtrx, ntrx);
-    if (trz && dtrz != trz) copy_out(*s, trz, dtrz, ntrz);
+    copy_out(*s, width, s->width);
+    if (trx && dtrx != trx) copy_n(trx, dtrx, ntrx);
+    if (trz && dtrz != trz) copy_n(trz, dtrz, ntrz);
     read_map_scalars(*s, *p, sc);
     if (trx && dtrx != trx) cudaFree(dtrx);
     if (trz && dtrz != trz) cudaFree(dtrz);
@@ -500,17 +595,19 @@ int apm_lcl_solver_device_field(apm_lcl_solver *h, const char *name, double **pt
     if (!h || !h->s || !name || !ptr) throw CudaError{"NULL argument"};
     Solver &s = *h->s;
     const std::string n(name);
+    // every array is returned as the rows this rank owns (all of them unless the solver is striped)
     double *p = nullptr;
-    size_t c = s.n;
-    if (n == "pressure") p = s.x;
-    else if (n == "width") p = s.width;
-    else if (n == "tx") p = s.tx;
-    else if (n == "tz") p = s.tz;
-    else if (n == "txl") { p = s.txl; c = s.nz; }
+    size_t c = s.own_cells();
+    if (n == "pressure") p = s.own(s.x);
+    else if (n == "width") p = s.own(s.width);
+    else if (n == "tx") p = s.own(s.tx);
+    else if (n == "tz") p = s.own(s.tz);
+    else if (n == "txl") { p = s.txl + s.zlo; c = (size_t)(s.zhi - s.zlo); }
     else if (n == "tzb") { p = s.tzb; c = s.nx; }
-    else if (n == "r") p = s.r;       // PCG scratch vectors: with time_kernel("vcycle") they give z = M^-1 r
-    else if (n == "q") p = s.q;       // (r in, q out), which the symmetry test of the preconditioner uses
-    else if (n == "nlevels") { p = s.x; c = s.levels.size(); }   // count carries the answer
+    else if (n == "r") p = s.own(s.r);       // PCG scratch vectors: with time_kernel("vcycle") they give z = M^-1 r
+    else if (n == "q") p = s.own(s.q);       // (r in, q out), which the symmetry test of the preconditioner uses
+    else if (n == "nlevels") { p = s.own(s.x); c = s.levels.size(); }   // count carries the answer
+    else if (n == "gather_level") { p = s.own(s.x); c = (size_t)s.gather_level; }
     else if (n.size() > 3 && n[0] == 'L' && n.find('.') != std::string::npos) {
         // diagnostics: "L<l>.<array>" = a stored coarse operator array (C S E N NE NW, l >= 1) or an
         // interpolation weight array of level l to l+1 (hw he vs vn csw cse cnw cne th tv tc)
@@ -519,29 +616,36 @@ int apm_lcl_solver_device_field(apm_lcl_solver *h, const char *name, double **pt
         const std::string arr = n.substr(dot + 1);
         if (l >= s.levels.size()) throw CudaError{"no such level"};
         Level &L = s.levels[l];
-        c = L.n;
-        if (arr == "nz") { p = s.x; c = (size_t)L.nz; }
-        else if (arr == "nx") { p = s.x; c = (size_t)L.nx; }
-        else if (arr == "C") p = L.C;
-        else if (arr == "S") p = L.S;
-        else if (arr == "E") p = L.E;
-        else if (arr == "N") p = L.N;
-        else if (arr == "NE") p = L.NE;
-        else if (arr == "NW") p = L.NW;
-        else {
+        c = L.own_cells();
+        const size_t off = (size_t)L.zlo * L.nx;
+        if (arr == "nz") { p = s.own(s.x); c = (size_t)L.nz; }
+        else if (arr == "nx") { p = s.own(s.x); c = (size_t)L.nx; }
+        else if (arr == "zlo") { p = s.own(s.x); c = (size_t)L.zlo; }
+        else if (arr == "zhi") { p = s.own(s.x); c = (size_t)L.zhi; }
+        else if (l == 0) throw CudaError{"the fine level stores no 9-point operator"};
+        else if (arr == "C") p = L.C + off;
+        else if (arr == "S") p = L.S + off;
+        else if (arr == "E") p = L.E + off;
+        else if (arr == "N") p = L.N + off;
+        else if (arr == "NE") p = L.NE + off;
+        else if (arr == "NW") p = L.NW + off;
+        if (!p) {
             if (l + 1 >= s.levels.size()) throw CudaError{"no weights on the coarsest level"};
-            c = s.levels[l + 1].n;
-            if (arr == "hw") p = L.w.hw;
-            else if (arr == "he") p = L.w.he;
-            else if (arr == "vs") p = L.w.vs;
-            else if (arr == "vn") p = L.w.vn;
-            else if (arr == "csw") p = L.w.csw;
-            else if (arr == "cse") p = L.w.cse;
-            else if (arr == "cnw") p = L.w.cnw;
-            else if (arr == "cne") p = L.w.cne;
-            else if (arr == "th") p = L.w.th;
-            else if (arr == "tv") p = L.w.tv;
-            else if (arr == "tc") p = L.w.tc;
+            const size_t cnx = (size_t)s.levels[l + 1].nx, woff = (size_t)L.czlo * cnx;
+            c = (size_t)(L.czhi - L.czlo) * cnx;
+            double *w = nullptr;
+            if (arr == "hw") w = L.w.hw;
+            else if (arr == "he") w = L.w.he;
+            else if (arr == "vs") w = L.w.vs;
+            else if (arr == "vn") w = L.w.vn;
+            else if (arr == "csw") w = L.w.csw;
+            else if (arr == "cse") w = L.w.cse;
+            else if (arr == "cnw") w = L.w.cnw;
+            else if (arr == "cne") w = L.w.cne;
+            else if (arr == "th") w = L.w.th;
+            else if (arr == "tv") w = L.w.tv;
+            else if (arr == "tc") w = L.w.tc;
+            if (w) p = w + woff;
         }
         if (!p) throw CudaError{"unknown or absent level array"};
     }
@@ -572,12 +676,12 @@ int apm_lcl_solver_time_kernel(apm_lcl_solver *h, const char *name, int reps, do
             // s.ap holds the map only after a solve that staged a HOST map and did not use it as residual scratch
             if (!s.ap_valid) throw CudaError{"time_kernel(\"conductance\") needs a solve from a host map without the residual field"};
             launch_conductance(s, s.last_params, s.ap);
-            b = 32.0 * (double)s.n;
+            b = 32.0 * (double)s.own_cells();
         }
         if (b < 0 && n == "flux") {
             FluxOut fo{s.r, s.d, s.q, s.z, nullptr};
             launch_flux(s, s.last_params, s.x, BoundaryValues{0, 0, 0, 0}, fo);
-            b = 64.0 * (double)s.n;
+            b = 64.0 * (double)s.own_cells();
         }
         if (b < 0) throw CudaError{"unknown kernel name"};
         return b;

@@ -90,14 +90,27 @@ inline int div_up(long long a, long long b) { return (int)((a + b - 1) / b); }
 //        and C = S + sum of the eight couplings.  A x is always evaluated as
 //        S x_p + sum g (x_p - x_q): a pocket of open cells behind ~1e-14-relative leak conductances
 //        keeps its leak information instead of losing it to cancellation (tools/proto_gth.py).
+//
+// Row strips (one map on several GPUs): a level is either striped -- rank k owns the contiguous
+// rows [zlo, zhi) and keeps kHalo ghost rows either side, filled by its neighbours through peer memory
+// (dist.cuh) -- or replicated on every rank (zlo = 0, zhi = nz).  Every array pointer of a striped level is
+// a VIRTUAL base: element (z, x) of the global grid sits at p[z * nx + x] for the rows a rank holds, so no
+// kernel translates indices; nz, nx stay the global dimensions (they decide where the physical boundary
+// is), zlo/zhi say which rows a kernel writes and reduces over.  One GPU is the case zlo = 0, zhi = nz.
+constexpr int kHalo = 6;   // ghost rows kept either side of a strip (the fine down leg reads 4 + 1 face row)
 struct Fine5 {
     const double *tx, *tz, *txl, *tzb;
     int nz, nx;
+    int zlo, zhi;
 };
 struct Coarse9 {
     const double *C, *S, *E, *N, *NE, *NW;
     int nz, nx;
+    int zlo, zhi;
 };
+// rows of a striped level a rank may READ: its own plus the ghost rows it holds, inside the grid
+__host__ __device__ inline int read_lo(int zlo) { return zlo - kHalo > 0 ? zlo - kHalo : 0; }
+__host__ __device__ inline int read_hi(int zhi, int nz) { return zhi + kHalo < nz ? zhi + kHalo : nz; }
 
 // interpolation weights fine(level l) <- coarse(level l+1), one entry per coarse 2x2 block
 // (Z,X): hw/he for the h-edge point (2Z,2X+1), vs/vn for the v-edge point (2Z+1,2X),
@@ -107,14 +120,22 @@ struct Weights {
     double *hw, *he, *vs, *vn, *csw, *cse, *cnw, *cne, *th, *tv, *tc;
 };
 
+constexpr int kMaxRanks = 16;
+
 struct Level {
     int nz = 0, nx = 0;
-    size_t n = 0;
+    size_t n = 0;              // cells of the whole level
+    int zlo = 0, zhi = 0;      // rows this rank owns (0, nz unless the level is striped)
+    bool striped = false;      // rows are dealt to the ranks (else every rank holds the whole level)
+    int cut[kMaxRanks + 1]{};  // striped: rank k owns rows [cut[k], cut[k+1])
+    int czlo = 0, czhi = 0;    // coarse rows (next level's numbering) this rank computes: weights, restriction
+    int ccut[kMaxRanks + 1]{}; // the same for every rank (the weight arrays are striped by these)
     // coarse levels only
     double *C = nullptr, *S = nullptr, *E = nullptr, *N = nullptr, *NE = nullptr, *NW = nullptr;
     double *x = nullptr, *b = nullptr, *r = nullptr;
     Weights w{};   // weights to the NEXT coarser level (absent on the coarsest)
-    Coarse9 view9() const { return Coarse9{C, S, E, N, NE, NW, nz, nx}; }
+    Coarse9 view9() const { return Coarse9{C, S, E, N, NE, NW, nz, nx, zlo, zhi}; }
+    size_t own_cells() const { return (size_t)(zhi - zlo) * nx; }
 };
 
 // PCG scalars live on the device; kernels read alpha/beta from here, the host only polls.
@@ -127,6 +148,7 @@ struct PcgState {
     double bb, bs;      // same for the right-hand side
     double tol2;        // rel_tol^2
     double dx, dx_prev, dx_prev2; // max |alpha d_i| of the last three updates (pointwise change of the iterate)
+    double dx_part;     // this rank's share of the latest one (its strip), combined over ranks by the next down leg
     double dx_tol;      // both must be <= dx_tol (absolute, = 2.5e-7 * pressure scale) before stopping
     int res_ok;         // number of iterations at which both residual-norm tests have passed
     int converged;      // set on device when all tests pass
@@ -135,6 +157,33 @@ struct PcgState {
 };
 
 constexpr int kMaxPartials = 4096;   // per-reduction partial slots (>= any grid we launch)
+
+// ---------------------------------------------------------------------------------------------
+// One map on several GPUs: what the ranks of a striped solve write into each other's memory.  Every rank
+// allocates ONE slab with the same layout, exports it (CUDA IPC) and maps the slabs of the others; a
+// pointer into the own slab plus peer_off[k] is the same object on rank k.  All remote accesses are
+// STORES into the peer's memory followed by a flag store; every wait polls LOCAL memory (peer loads bypass
+// L2 and may be served stale from L1).  Counters only grow, every rank runs the same sequence of kernels,
+// and a wait refers to a kernel the peer enqueued no later than this one: no cycle, hence no deadlock;
+// waits are bounded anyway (dist.cuh) and raise `error` instead of hanging the GPU.
+constexpr int kGatherMax = 12;   // doubles per rank in one gather
+struct PeerWindow {
+    unsigned long long halo_flag[2];              // [0] written by the rank below, [1] by the rank above: exchange count
+    unsigned long long gather_flag[kMaxRanks];    // written by rank k: its gather count
+    unsigned long long bcast_flag[kMaxRanks];     // written by rank k: its row-broadcast count
+    double gather_slot[2][kMaxRanks][kGatherMax]; // rank k's values, double buffered by the parity of the count
+};
+struct DistLocal {                                // local bookkeeping of the same sequence (never written by peers)
+    unsigned long long halo_seq, gather_seq, bcast_seq;
+    unsigned int block_counter[4];                // "last block done" of the exchange kernels
+    int error;                                    // a wait timed out
+};
+struct Dist {
+    int rank = 0, world = 1;
+    PeerWindow *win[kMaxRanks]{};     // every rank's window as THIS rank addresses it (win[rank] is local)
+    long long peer_off[kMaxRanks]{};  // bytes from an address in the own slab to the same object of rank k
+    DistLocal *local = nullptr;
+};
 
 struct Reducer {
     double *partials = nullptr;      // [kSlots][kMaxPartials]
@@ -162,6 +211,16 @@ struct TailArgs {
 struct Solver {
     int device = 0, nx = 0, nz = 0;
     size_t n = 0;
+    // strips (world == 1: one strip holding every row)
+    int rank = 0, world = 1;
+    int zlo = 0, zhi = 0;           // fine rows this rank owns
+    int gather_level = 0;           // first level every rank holds whole (levels below it are striped); 0: none striped
+    Dist dist{};
+    char *slab = nullptr;           // every device array of the solver lives in this one allocation
+    size_t slab_bytes = 0;
+    void *peer_slab[kMaxRanks]{};   // the other ranks' slabs as mapped here
+    bool peer_ipc[kMaxRanks]{};     // mapped through CUDA IPC (a rank of another process) rather than addressed directly
+    bool connected = false;
     cudaStream_t stream = nullptr;
     cudaStream_t copy_stream = nullptr;   // device -> host copies that can run beside the solve
     int num_sms = 148;
@@ -193,8 +252,54 @@ struct Solver {
     bool ap_valid = false;         // ap holds the staged aperture map of the last solve (not flux scratch)
     bool down_configured = false;   // k_down5 opted in to >48 KB dynamic shared memory on this device
     apm_lcl_params last_params{};
-    Fine5 view5() const { return Fine5{tx, tz, txl, tzb, nz, nx}; }
+    Fine5 view5() const { return Fine5{tx, tz, txl, tzb, nz, nx, zlo, zhi}; }
+    size_t own_cells() const { return (size_t)(zhi - zlo) * nx; }
+    double *own(double *p) const { return p + (size_t)zlo * nx; }   // first owned element of a fine-level array
 };
+
+// Bump allocator over the solver's slab.  The layout runs twice: a counting pass (base == nullptr) that
+// only measures, then the real one.  Every rank lays out the same sizes in the same order, so an object has
+// the same offset in every rank's slab (what Dist::peer_off relies on).
+struct Arena {
+    char *base = nullptr;
+    size_t used = 0;
+    void *take_bytes(size_t bytes)
+    {
+        used = (used + 255) & ~(size_t)255;
+        void *p = base + used;   // counting pass: a fake address nobody dereferences
+        used += bytes ? bytes : 8;
+        return p;
+    }
+    double *take(size_t count) { return (double *)take_bytes(count * sizeof(double)); }
+    // array of `pitch`-wide rows: striped (every rank allocates the tallest strip plus ghost rows and gets the
+    // virtual base that makes global row numbers work) or whole
+    double *take_rows(int pitch, int nz, bool striped, const int *cut, int rank, int world)
+    {
+        if (!striped) return take((size_t)nz * pitch);
+        int tallest = 0;
+        for (int k = 0; k < world; k++) tallest = cut[k + 1] - cut[k] > tallest ? cut[k + 1] - cut[k] : tallest;
+        double *p = take((size_t)(tallest + 2 * kHalo) * pitch);
+        return p - (long long)(cut[rank] - kHalo) * pitch;
+    }
+};
+
+// peer.cu --------------------------------------------------------------------------------------
+constexpr int kPeerHandleBytes = 128;
+void slab_create(Solver &s, size_t bytes, void *handle_out);   // one zeroed allocation (+ its IPC handle if world > 1)
+void slab_connect(Solver &s, const void *handles);             // maps the peers' slabs, fills s.dist
+void slab_disconnect(Solver &s);
+void slab_destroy(Solver &s);
+struct HaloSet {
+    double *a[12];
+    int count = 0;
+    void add(double *p) { a[count++] = p; }
+};
+// Ghost rows of striped arrays (row pitch `pitch`, strips cut[0..world]): every rank stores its lowest `dhi`
+// rows into the upper ghost rows of the rank below and its highest `dlo` rows into the lower ghost rows of
+// the rank above, then waits for its own ghosts.  A no-op when world == 1.
+void halo_exchange(Solver &s, const HaloSet &hs, int pitch, const int *cut, int dlo, int dhi, const PcgState *st);
+// Rows [cut[rank], cut[rank+1]) of REPLICATED arrays go to every other rank (an all-gather by stores).
+void row_broadcast(Solver &s, const HaloSet &hs, int pitch, const int *cut, const PcgState *st);
 
 // conductance.cu -------------------------------------------------------------------------------
 // scal layout written by the conductance kernel
@@ -204,8 +309,8 @@ void launch_conductance(Solver &s, const apm_lcl_params &p, const double *ap_dev
 void export_reference_layout(Solver &s, double *trx_dev, double *trz_dev);   // [nz][nx+1], [nz+1][nx]
 
 // mg_setup.cu ----------------------------------------------------------------------------------
-void mg_allocate(Solver &s);
-void mg_free(Solver &s);
+void mg_plan(Solver &s);                  // level sizes, which levels are striped and where the strips are cut
+void mg_allocate(Solver &s, Arena &a);    // takes every level's arrays from the arena (called for both passes)
 void mg_setup(Solver &s);   // weights + Galerkin operators + coarsest inverse, from s.tx/s.tz
 
 // mg_cycle.cu ----------------------------------------------------------------------------------

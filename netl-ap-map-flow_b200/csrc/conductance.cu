@@ -75,18 +75,19 @@ __device__ __forceinline__ double width_of(double a_clamped, const CondParams &p
 }
 
 __global__ void __launch_bounds__(kBlock)
-k_conductance(const double *__restrict__ ap, int nz, int nx, CondParams p, double *__restrict__ width,
+k_conductance(const double *__restrict__ ap, int nz, int nx, int zlo, int zhi, CondParams p, double *__restrict__ width,
               double *__restrict__ tx, double *__restrict__ tz, double *__restrict__ txl,
-              double *__restrict__ tzb, double *partials, unsigned int *counter, double *scal)
+              double *__restrict__ tzb, double *partials, unsigned int *counter, double *scal, Dist dc)
 {
+    // a strip [zlo, zhi) reads the aperture rows zlo-1 .. zhi (corner points), global row numbers throughout
     const ApView A{ap, nz, nx, p.high, p.low};
-    const Tiles tiles(nz, nx);
+    const Tiles tiles(zlo, zhi, nx);
     double acc[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};   // raw sum, clamped sum, -min_pos(as max of neg), max, zeros, masked
     double vmin = 1e300, vmax = -1e300;
     for (long long t = blockIdx.x; t < tiles.ntiles; t += gridDim.x) {
         int z, x;
         tiles.cell(t, z, x);
-        if (z >= nz || x >= nx) continue;
+        if (z >= zhi || x >= nx) continue;
         const size_t i = (size_t)z * nx + x;
         const double raw = ap[i];
         const double a = clampa(raw, p.high, p.low);
@@ -166,12 +167,23 @@ k_conductance(const double *__restrict__ ap, int nz, int nx, CondParams p, doubl
             mn = fmin(mn, ldcg(&partials[6 * kMaxPartials + b]));
             mx = fmax(mx, ldcg(&partials[7 * kMaxPartials + b]));
         }
-        scal[SC_RAW_SUM] = tot[0];
-        scal[SC_CLAMP_SUM] = tot[1];
+        // the strips' sums, counters and extrema in rank order: every rank ends up with the same scalars
+        const double mine[8] = {tot[0], tot[1], tot[2], tot[3], tot[4], tot[5], mn, mx};
+        double all[kMaxRanks][8];
+        dist_gather<8>(dc, mine, all);
+        double sum[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+        mn = 1e300; mx = -1e300;
+        for (int r = 0; r < dc.world; r++) {
+            for (int k = 0; k < 6; k++) sum[k] += all[r][k];
+            mn = fmin(mn, all[r][6]);
+            mx = fmax(mx, all[r][7]);
+        }
+        scal[SC_RAW_SUM] = sum[0];
+        scal[SC_CLAMP_SUM] = sum[1];
         scal[SC_MIN_POS] = mn == 1e300 ? 0.0 : mn;
         scal[SC_MAX] = mx;
-        scal[SC_ZEROS] = tot[4];
-        scal[SC_MASKED] = tot[5];
+        scal[SC_ZEROS] = sum[4];
+        scal[SC_MASKED] = sum[5];
     });
 }
 
@@ -183,12 +195,21 @@ void launch_conductance(Solver &s, const apm_lcl_params &p, const double *ap_dev
     const double diam = s.nx * p.voxel_size * p.avg_factor, leng = s.nz * p.voxel_size * p.avg_factor;
     c.dx = diam / s.nx; c.dz = leng / s.nz;
     c.side = p.outlet_side;
-    const int grid = grid_for(s, s.nz, s.nx, 8);
-    LAUNCH(k_conductance, grid, kBlock, 0, s.stream, ap_dev, s.nz, s.nx, c, s.width, s.tx, s.tz, s.txl, s.tzb,
-           s.red, s.red_counters, s.scal);
+    const int grid = grid_for(s, s.zhi - s.zlo, s.nx, 8);
+    LAUNCH(k_conductance, grid, kBlock, 0, s.stream, ap_dev, s.nz, s.nx, s.zlo, s.zhi, c, s.width, s.tx, s.tz, s.txl, s.tzb,
+           s.red, s.red_counters, s.scal, s.dist);
+    if (s.levels[0].striped) {   // the faces are read by every fine-level kernel up to 5 rows beyond a strip
+        HaloSet hs;
+        hs.add(s.tx);
+        hs.add(s.tz);
+        halo_exchange(s, hs, s.nx, s.levels[0].cut, kHalo, kHalo, nullptr);
+        HaloSet h1;
+        h1.add(s.txl);
+        halo_exchange(s, h1, 1, s.levels[0].cut, kHalo, kHalo, nullptr);
+    }
 }
 
-// TRX(1:NZ,0:NX) / TRZ(0:NZ,1:NX) in the reference's own layout, for the parity tests
+// TRX(1:NZ,0:NX) / TRZ(0:NZ,1:NX) in the reference's own layout, for the parity tests (single-GPU solvers)
 __global__ void k_export_layout(Fine5 v, double *__restrict__ trx, double *__restrict__ trz)
 {
     const F5 A{v};

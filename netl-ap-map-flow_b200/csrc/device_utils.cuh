@@ -2,6 +2,7 @@
 #pragma once
 
 #include "common.cuh"
+#include "dist.cuh"
 
 namespace lcl {
 
@@ -241,22 +242,24 @@ __device__ __forceinline__ void grid_max_finalize(double v, double *partials, un
     }
 }
 
-// tile iteration: 1-D grid, each block walks 32x8 tiles of an nz x nx grid (one cell per thread)
+// tile iteration: 1-D grid, each block walks 32x8 tiles of the rows [zlo, zhi) of a grid nx wide (one cell per
+// thread; cells with z >= zhi or x >= nx are the caller's to skip)
 struct Tiles {
-    int tiles_x;
+    int tiles_x, zlo;
     long long ntiles;
-    __device__ __forceinline__ Tiles(int nz, int nx)
+    __device__ __forceinline__ Tiles(int zlo_, int zhi, int nx) : zlo(zlo_)
     {
         tiles_x = (nx + kTileX - 1) / kTileX;
-        ntiles = (long long)tiles_x * ((nz + kTileZ - 1) / kTileZ);
+        ntiles = (long long)tiles_x * ((zhi - zlo + kTileZ - 1) / kTileZ);
     }
     __device__ __forceinline__ void cell(long long t, int &z, int &x) const
     {
-        z = (int)(t / tiles_x) * kTileZ + (threadIdx.x >> 5);
+        z = zlo + (int)(t / tiles_x) * kTileZ + (threadIdx.x >> 5);
         x = (int)(t % tiles_x) * kTileX + (threadIdx.x & 31);
     }
 };
 
+// grid for a kernel that walks `nz` rows (the rows a rank owns) of a level nx wide
 inline int grid_for(const Solver &s, int nz, int nx, int blocks_per_sm = 8)
 {
     long long tiles = (long long)div_up(nx, kTileX) * div_up(nz, kTileZ);

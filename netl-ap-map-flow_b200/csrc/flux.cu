@@ -16,18 +16,18 @@ struct FluxParams {
 
 __global__ void __launch_bounds__(kBlock)
 k_flux(Fine5 v, const double *__restrict__ p, const double *__restrict__ width, BoundaryValues bv, FluxParams fp,
-       FluxOut o, double *partials, unsigned int *counter, double *scal)
+       FluxOut o, double *partials, unsigned int *counter, double *scal, Dist dc)
 {
     const F5 A{v};
     const int nz = v.nz, nx = v.nx;
-    const Tiles tiles(nz, nx);
+    const Tiles tiles(v.zlo, v.zhi, nx);   // a strip's own rows; p has a ghost row either side
     double acc[1] = {0.0};            // outlet FLOW
     double best = -1.0, best_signed = 0.0;
     long long best_idx = -1;          // MAXLOC: first maximum in cell order
     for (long long t = blockIdx.x; t < tiles.ntiles; t += gridDim.x) {
         int z, x;
         tiles.cell(t, z, x);
-        if (z >= nz || x >= nx) continue;
+        if (z >= v.zhi || x >= nx) continue;
         const size_t i = (size_t)z * nx + x;
         const double pc = p[i];
         const double pl = x > 0 ? p[i - 1] : bv.left;
@@ -87,7 +87,18 @@ k_flux(Fine5 v, const double *__restrict__ p, const double *__restrict__ width, 
                 bv_ = cv; bs_ = ldcg(&partials[2 * kMaxPartials + b]); bi_ = ci;
             }
         }
-        scal[SC_FLOW] = tot[0];
+        // strips: outlet flow summed, MAXLOC over the ranks' candidates (largest value, first cell), in rank order
+        const double mine[4] = {tot[0], bv_, bs_, bi_};
+        double all[kMaxRanks][4];
+        dist_gather<4>(dc, mine, all);
+        double flow = 0.0;
+        bv_ = -1.0; bs_ = 0.0; bi_ = -1.0;
+        for (int r = 0; r < dc.world; r++) {
+            flow += all[r][0];
+            const double cv = all[r][1], ci = all[r][3];
+            if (ci >= 0.0 && (cv > bv_ || (cv == bv_ && (ci < bi_ || bi_ < 0.0)))) { bv_ = cv; bs_ = all[r][2]; bi_ = ci; }
+        }
+        scal[SC_FLOW] = flow;
         scal[SC_MAXRES_ABS] = bv_;
         scal[SC_MAXRES_SIGNED] = bs_;
     });
@@ -113,10 +124,10 @@ void launch_flux(Solver &s, const apm_lcl_params &p, const double *pres, const B
     FluxParams fp;
     fp.rho_over_mu = p.density / p.viscosity;
     fp.side = p.outlet_side;
-    const int g0 = grid_for(s, s.nz, s.nx, 8);
+    const int g0 = grid_for(s, s.zhi - s.zlo, s.nx, 8);
     LAUNCH(k_flux, g0, kBlock, 0, s.stream, s.view5(), pres, (const double *)s.width, bv, fp, o,
-           s.red + 10 * kMaxPartials, s.red_counters + 3, s.scal);
-    if (o.res) LAUNCH(k_normalise, s.num_sms * 8, 256, 0, s.stream, o.res, s.n, (const double *)s.scal);
+           s.red + 10 * kMaxPartials, s.red_counters + 3, s.scal, s.dist);
+    if (o.res) LAUNCH(k_normalise, s.num_sms * 8, 256, 0, s.stream, s.own(o.res), s.own_cells(), (const double *)s.scal);
 }
 
 void launch_affine(Solver &s, double *x, size_t n, double scale, double shift)

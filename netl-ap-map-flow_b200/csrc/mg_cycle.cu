@@ -28,16 +28,18 @@ __device__ __forceinline__ bool stopped(const PcgState *st)
 // -------------------------------------------------------------------------------- coarse levels
 __global__ void __launch_bounds__(kBlock)
 k_residual9(Coarse9 v, const double *__restrict__ b, const double *__restrict__ x, double *__restrict__ r,
-            const PcgState *st)
+            int z0, int z1, const PcgState *st)
 {
+    // rows [z0, z1): a strip also computes the row below its own (the restriction of its first coarse row
+    // reads it), from the ghost rows of x and of the operator
     if (stopped(st)) return;
     const C9 A{v};
     const int nz = v.nz, nx = v.nx;
-    const Tiles tiles(nz, nx);
+    const Tiles tiles(z0, z1, nx);
     for (long long t = blockIdx.x; t < tiles.ntiles; t += gridDim.x) {
         int z, xx;
         tiles.cell(t, z, xx);
-        if (z >= nz || xx >= nx) continue;
+        if (z >= z1 || xx >= nx) continue;
         const size_t i = (size_t)z * nx + xx;
         const double xi = x[i];
         double s = b[i] - A.S(z, xx) * xi;
@@ -110,14 +112,15 @@ static_assert(2 * (kSm9Smem + 1024) <= 227 * 1024, "two blocks per SM");
 
 __device__ __forceinline__ void stage_tile9(double *st, const Coarse9 &v, const double *__restrict__ b, int z0, int x0)
 {
-    const int nz = v.nz, nx = v.nx;
+    // rows a rank may read: its strip plus ghost rows (the whole grid on one GPU); rows it owns: [zlo, zhi)
+    const int nx = v.nx, rlo = read_lo(v.zlo), rhi = read_hi(v.zhi, v.nz), zhi = v.zhi;
     double *sE = st, *sN = st + kStPlane, *sNE = st + 2 * kStPlane, *sNW = st + 3 * kStPlane;
     double *sb = st + 4 * kStPlane, *sC = sb + kStTile;
 #pragma unroll 2
     for (int k = threadIdx.x; k < kStPlane; k += kSmThreads) {
         const int r = k / kStCols, cc = k % kStCols;
         const int z = z0 - 1 + r, x = x0 - 1 + cc, q = split_pos<kStCols>(r, cc);
-        const bool in = z >= 0 && z < nz && x >= 0 && x < nx;
+        const bool in = z >= rlo && z < rhi && x >= 0 && x < nx;
         const size_t i = in ? (size_t)z * nx + x : 0;
         cp_async8(&sE[q], v.E + i, in);
         cp_async8(&sN[q], v.N + i, in);
@@ -128,7 +131,7 @@ __device__ __forceinline__ void stage_tile9(double *st, const Coarse9 &v, const 
     for (int k = threadIdx.x; k < kStTile; k += kSmThreads) {
         const int lz = k / kSmTX, lx = k % kSmTX;
         const int z = z0 + lz, x = x0 + lx, q = split_pos<kSmTX>(lz, lx);
-        const bool in = z < nz && x < nx;
+        const bool in = z < zhi && x < nx;
         const size_t i = in ? (size_t)z * nx + x : 0;
         cp_async8(&sb[q], b + i, in);
         cp_async8(&sC[q], v.C + i, in);
@@ -164,27 +167,28 @@ constexpr int kPrStage = kSmH * kSmW + kPrE + 8 * kPrB;
 constexpr size_t kSm9SmemUp = kSm9Smem + (size_t)(kPrStage + (kPrStage & 1)) * sizeof(double);
 static_assert(2 * (kSm9SmemUp + 1024) <= 227 * 1024, "two blocks per SM");
 
+// rlo, rhi: rows of xin this rank holds; wlo, whi: coarse rows of the weights and of e it holds
 __device__ __forceinline__ void stage_prolong9(double *st, const double *__restrict__ xin, const Weights &w,
-                                               const double *__restrict__ e, int nzc, int nxc, int z0, int x0, int nz,
-                                               int nx)
+                                               const double *__restrict__ e, int wlo, int whi, int nxc, int z0, int x0,
+                                               int rlo, int rhi, int nx)
 {
     double *sXin = st, *sE = st + kSmH * kSmW, *sW = sE + kPrE;
     const int zr = z0 - 2, xr = x0 - 2, bz0 = zr >> 1, bx0 = xr >> 1;   // arithmetic shift: -2 >> 1 == -1
 #pragma unroll 2
     for (int k = threadIdx.x; k < kSmH * kSmW; k += kSmThreads) {
         const int z = zr + k / kSmW, x = xr + k % kSmW;
-        const bool in = z >= 0 && z < nz && x >= 0 && x < nx;
+        const bool in = z >= rlo && z < rhi && x >= 0 && x < nx;
         cp_async8(&sXin[k], xin + (in ? (size_t)z * nx + x : 0), in);
     }
     for (int k = threadIdx.x; k < kPrE; k += kSmThreads) {
         const int bz = bz0 + k / (kPrBW + 1), bx = bx0 + k % (kPrBW + 1);
-        const bool in = bz >= 0 && bz < nzc && bx >= 0 && bx < nxc;
+        const bool in = bz >= wlo && bz < whi && bx >= 0 && bx < nxc;
         cp_async8(&sE[k], e + (in ? (size_t)bz * nxc + bx : 0), in);
     }
 #pragma unroll
     for (int k = threadIdx.x; k < kPrB; k += kSmThreads) {
         const int bz = bz0 + k / kPrBW, bx = bx0 + k % kPrBW;
-        const bool in = bz >= 0 && bz < nzc && bx >= 0 && bx < nxc;
+        const bool in = bz >= wlo && bz < whi && bx >= 0 && bx < nxc;
         const size_t b = in ? (size_t)bz * nxc + bx : 0;
         cp_async8(&sW[k], w.hw + b, in);
         cp_async8(&sW[kPrB + k], w.he + b, in);
@@ -240,30 +244,33 @@ __device__ __forceinline__ void prolong_staged9(double *sx, const double *st, in
 template <bool ZERO_INIT, bool PROLONG, bool FORWARD>
 __global__ void __launch_bounds__(256, 2)
 k_smooth9(Coarse9 v, const double *__restrict__ b, const double *__restrict__ xin, double *__restrict__ xout, int nu,
-          Weights w, const double *__restrict__ e, int nzc, int nxc, const PcgState *st)
+          Weights w, const double *__restrict__ e, int nzc, int nxc, int wlo, int whi, const PcgState *st)
 {
     if (stopped(st)) return;
     const int nz = v.nz, nx = v.nx;
+    // a strip walks the tiles of its own rows [zlo, zhi) (cut at multiples of the tile height, mg_plan) and
+    // reads the rows [rlo, rhi) it holds: the frame of a tile at a cut is the neighbour's ghost rows
+    const int zlo = v.zlo, zhi = v.zhi, rlo = read_lo(zlo), rhi = read_hi(zhi, nz);
     constexpr int W = kSmW, H = kSmH;
     LCL_DYNAMIC_SMEM(double, smem);
     double *stage = smem, *sx = smem + 4 * kStPlane + 2 * kStTile;   // sx at a 16-byte aligned offset
     double *stage2 = sx + kSmH * kSmW;                               // PROLONG only
-    const int tiles_x = (nx + kSmTX - 1) / kSmTX, tiles_z = (nz + kSmTZ - 1) / kSmTZ;
+    const int tiles_x = (nx + kSmTX - 1) / kSmTX, tiles_z = (zhi - zlo + kSmTZ - 1) / kSmTZ;
     const long long ntiles = (long long)tiles_x * tiles_z;
     const int tid = threadIdx.x;
     const int a = tid >> 5, c = tid & 31;
     if (blockIdx.x < ntiles) {
-        const int z0 = (int)(blockIdx.x / tiles_x) * kSmTZ, x0 = (int)(blockIdx.x % tiles_x) * kSmTX;
+        const int z0 = zlo + (int)(blockIdx.x / tiles_x) * kSmTZ, x0 = (int)(blockIdx.x % tiles_x) * kSmTX;
         stage_tile9(stage, v, b, z0, x0);
-        if (PROLONG) stage_prolong9(stage2, xin, w, e, nzc, nxc, z0, x0, nz, nx);
+        if (PROLONG) stage_prolong9(stage2, xin, w, e, wlo, whi, nxc, z0, x0, rlo, rhi, nx);
     }
     for (long long t = blockIdx.x; t < ntiles; t += gridDim.x) {
-        const int z0 = (int)(t / tiles_x) * kSmTZ, x0 = (int)(t % tiles_x) * kSmTX;
+        const int z0 = zlo + (int)(t / tiles_x) * kSmTZ, x0 = (int)(t % tiles_x) * kSmTX;
         if (!PROLONG) {
             for (int k = tid; k < H * W; k += kSmThreads) {
                 const int zf = z0 + k / W - 2, xf = x0 + k % W - 2;
                 double val = 0.0;
-                if (!ZERO_INIT && zf >= 0 && zf < nz && xf >= 0 && xf < nx)
+                if (!ZERO_INIT && zf >= rlo && zf < rhi && xf >= 0 && xf < nx)
                     val = xin[(size_t)zf * nx + xf];     // never the array this launch writes: other tiles read it
                 sx[ZERO_INIT ? k : split_pos<W>(k / W, k % W)] = val;
             }
@@ -276,9 +283,9 @@ k_smooth9(Coarse9 v, const double *__restrict__ b, const double *__restrict__ xi
         __syncthreads();                                 // every operand is in registers or sx: the stages are free again
         if (t + gridDim.x < ntiles) {
             const long long tn = t + gridDim.x;
-            const int zn = (int)(tn / tiles_x) * kSmTZ, xn = (int)(tn % tiles_x) * kSmTX;
+            const int zn = zlo + (int)(tn / tiles_x) * kSmTZ, xn = (int)(tn % tiles_x) * kSmTX;
             stage_tile9(stage, v, b, zn, xn);
-            if (PROLONG) stage_prolong9(stage2, xin, w, e, nzc, nxc, zn, xn, nz, nx);
+            if (PROLONG) stage_prolong9(stage2, xin, w, e, wlo, whi, nxc, zn, xn, rlo, rhi, nx);
         }
         // the thread's block: framed rows 2a+2, 2a+3, columns 2c+2 (even, half index c+1) and 2c+3 (odd)
         double *pe0 = &sx[(2 * a + 2) * W + c + 1];      // even column
@@ -307,15 +314,26 @@ k_smooth9(Coarse9 v, const double *__restrict__ b, const double *__restrict__ xi
         for (int k = tid; k < kSmTZ * kSmTX; k += kSmThreads) {
             const int lz = k / kSmTX, lx = k % kSmTX;
             const int zf = z0 + lz, xf = x0 + lx;
-            if (zf < nz && xf < nx) xout[(size_t)zf * nx + xf] = sx[split_pos<W>(lz + 2, lx + 2)];
+            if (zf < zhi && xf < nx) xout[(size_t)zf * nx + xf] = sx[split_pos<W>(lz + 2, lx + 2)];
         }
         __syncthreads();
     }
 }
 
 // What the down leg's reduction decides: the PCG residual norms and the stopping rule.
-__device__ __forceinline__ void down_norms_finalize(PcgState *st, int init, const double (&tot)[2])
+__device__ __forceinline__ void down_norms_finalize(PcgState *st, int init, const double (&part)[2], const Dist &dc)
 {
+    // this strip's sums and its largest pointwise change of the last update (k_update), combined in rank order
+    const double mine[3] = {part[0], part[1], st->dx_part};
+    double all[kMaxRanks][3];
+    dist_gather<3>(dc, mine, all);
+    double tot[2] = {0.0, 0.0}, dx = 0.0;
+    for (int r = 0; r < dc.world; r++) {
+        tot[0] += all[r][0];
+        tot[1] += all[r][1];
+        dx = fmax(dx, all[r][2]);
+    }
+    st->dx = dx;
     st->rr = tot[0];
     st->rs = tot[1];
     if (init) {
@@ -368,11 +386,14 @@ template <int F, int H>
 __device__ __forceinline__ void stage_tile5(double *sb, double *stx, double *stz, const Fine5 &v,
                                             const double *__restrict__ b, int z0, int x0, int wy, int lane)
 {
-    const int nz = v.nz, nx = v.nx;
+    // rows this rank holds (strip + ghost rows; the whole grid on one GPU).  Row -1 of the grid is the bottom
+    // boundary face tzb; the row below a strip's ghost rows is not held and reads as 0 (it only feeds ghost
+    // cells nobody uses)
+    const int nx = v.nx, rlo = read_lo(v.zlo), rhi = read_hi(v.zhi, v.nz);
 #pragma unroll
     for (int row = wy; row < H; row += kDnWarps) {
         const int z = z0 + row - F;
-        const bool zin = z >= 0 && z < nz, zface = z >= -1 && z < nz;
+        const bool zin = z >= rlo && z < rhi, zface = zin || z == -1;
         const size_t zoff = zin ? (size_t)z * nx : 0;
         const double *brow = b + zoff, *txrow = v.tx + zoff, *tzrow = zin ? v.tz + zoff : v.tzb;
         const double *txl = v.txl + (zin ? z : 0);
@@ -391,18 +412,22 @@ __device__ __forceinline__ void stage_tile5(double *sb, double *stx, double *stz
 
 __global__ void __launch_bounds__(kDnThreads, 2)
 k_down5(Fine5 v, Weights w, const double *__restrict__ b, double *__restrict__ x, double *__restrict__ bc, int nzc,
-        int nxc, PcgState *st, int init, double *partials, unsigned int *counter)
+        int nxc, int czhi, PcgState *st, int init, double *partials, unsigned int *counter, Dist dc)
 {
     if (stopped(st)) return;
     constexpr int W = kDnW, H = kDnH, FL = kDnFL, TZ = kDnTZ, TX = kDnTX;
     LCL_DYNAMIC_SMEM(double, smem);
     double *sb = smem, *stx = smem + H * W, *stz = smem + 2 * H * W, *sx = smem + 3 * H * W;
-    const int nz = v.nz, nx = v.nx;
-    const int tiles_x = (nx + TX - 1) / TX, tiles_z = (nz + TZ - 1) / TZ;
+    // a strip tiles its own rows [zlo, zhi) (zlo even) and owns the coarse rows below czhi; cells exist for it
+    // in the rows [rlo, rhi) it holds.  The frame of a tile at a cut is recomputed from the ghost rows of b and
+    // of the faces exactly as inside the grid: the sweep is exact red/black, so the result does not depend on
+    // where tiles or strips are cut.
+    const int nz = v.nz, nx = v.nx, zlo = v.zlo, zhi = v.zhi, rlo = read_lo(zlo), rhi = read_hi(zhi, nz);
+    const int tiles_x = (nx + TX - 1) / TX, tiles_z = (zhi - zlo + TZ - 1) / TZ;
     const int lane = threadIdx.x & 31, wy = threadIdx.x >> 5;
     double acc[2] = {0.0, 0.0};
     for (long long t = blockIdx.x; t < (long long)tiles_x * tiles_z; t += gridDim.x) {
-        const int z0 = (int)(t / tiles_x) * TZ, x0 = (int)(t % tiles_x) * TX;
+        const int z0 = zlo + (int)(t / tiles_x) * TZ, x0 = (int)(t % tiles_x) * TX;
         stage_tile5<FL, H>(sb, stx, stz, v, b, z0, x0, wy, lane);
         // restriction weights of this thread's coarse points (rows wy, wy + 16 of the tile's 21 x 29) ride along
         constexpr int CR = (TZ / 2 + kDnWarps - 1) / kDnWarps;
@@ -412,7 +437,7 @@ k_down5(Fine5 v, Weights w, const double *__restrict__ b, double *__restrict__ x
 #pragma unroll
         for (int c = 0; c < CR; c++) {
             const int cr = wy + c * kDnWarps, Z = z0 / 2 + cr;
-            cin[c] = cr < TZ / 2 && lane < TX / 2 && Z < nzc && X < nxc;
+            cin[c] = cr < TZ / 2 && lane < TX / 2 && Z < czhi && X < nxc;
             wne[c] = wnw[c] = wse[c] = wsw[c] = 0.0;
             if (cin[c]) {
                 const size_t bk = (size_t)Z * nxc + X;
@@ -433,11 +458,11 @@ k_down5(Fine5 v, Weights w, const double *__restrict__ b, double *__restrict__ x
             const int z = z0 + lz, xx = x0 + lx, par = (lx + FL) & 1;
             const int p = dn_pos(lz + FL, lx + FL), pl = p + (par ? -32 : 31);
             double val = 0.0;
-            if (z >= 0 && z < nz && xx >= 0 && xx < nx) {
+            if (z >= rlo && z < rhi && xx >= 0 && xx < nx) {
                 const double bi = sb[p];
                 const double inv = 1.0 / ((stx[pl] + stx[p]) + (stz[p - W] + stz[p]));
                 val = bi * inv;
-                if (lz >= 0 && lz < TZ && lx >= 0 && lx < TX) { acc[0] += bi * bi; acc[1] += bi * bi * inv; }
+                if (lz >= 0 && lz < TZ && z < zhi && lx >= 0 && lx < TX) { acc[0] += bi * bi; acc[1] += bi * bi * inv; }
             }
             sx[p] = val;
         }
@@ -450,7 +475,7 @@ k_down5(Fine5 v, Weights w, const double *__restrict__ b, double *__restrict__ x
             const int z = z0 + lz, xx = x0 + lx, par = (lx + FL) & 1;
             const int p = dn_pos(lz + FL, lx + FL), pl = p + (par ? -32 : 31), pr = p + (par ? -31 : 32);
             double val = 0.0;
-            if (z >= 0 && z < nz && xx >= 0 && xx < nx) {
+            if (z >= rlo && z < rhi && xx >= 0 && xx < nx) {
                 const double tl = stx[pl], tr = stx[p], td = stz[p - W], tu = stz[p];
                 const double bi = sb[p];
                 double s = bi;
@@ -460,7 +485,7 @@ k_down5(Fine5 v, Weights w, const double *__restrict__ b, double *__restrict__ x
                 s += tu * sx[p + W];
                 const double inv = 1.0 / ((tl + tr) + (td + tu));
                 val = s * inv;
-                if (lz >= 0 && lz < TZ && lx >= 0 && lx < TX) { acc[0] += bi * bi; acc[1] += bi * bi * inv; }
+                if (lz >= 0 && lz < TZ && z < zhi && lx >= 0 && lx < TX) { acc[0] += bi * bi; acc[1] += bi * bi * inv; }
             }
             sx[p] = val;
         }
@@ -472,7 +497,7 @@ k_down5(Fine5 v, Weights w, const double *__restrict__ b, double *__restrict__ x
             if (lx > TX - 1) continue;
             const int z = z0 + lz, xx = x0 + lx, par = (lx + FL) & 1;
             const int p = dn_pos(lz + FL, lx + FL), pl = p + (par ? -32 : 31), pr = p + (par ? -31 : 32);
-            if (z >= 0 && z < nz && xx >= 0 && xx < nx) {
+            if (z >= rlo && z < rhi && xx >= 0 && xx < nx) {
                 const double xi = sx[p];
                 double s = sb[p];
                 s -= stx[pl] * (xi - sx[pl]);
@@ -486,7 +511,7 @@ k_down5(Fine5 v, Weights w, const double *__restrict__ b, double *__restrict__ x
 #pragma unroll
         for (int lz = wy; lz < TZ; lz += kDnWarps) {
             const int z = z0 + lz, xe = x0 + 2 * lane;
-            if (lane >= TX / 2 || z >= nz || xe >= nx) continue;
+            if (lane >= TX / 2 || z >= zhi || xe >= nx) continue;
             const size_t i = (size_t)z * nx + xe;
             const int p = dn_pos(lz + FL, 2 * lane + FL);      // even column; its right neighbour is at p + 32
             const double v0 = sx[p], v1 = sx[p + 32];
@@ -512,7 +537,7 @@ k_down5(Fine5 v, Weights w, const double *__restrict__ b, double *__restrict__ x
             }
         __syncthreads();
     }
-    grid_sum_finalize<2>(acc, partials, counter, [=](const double(&tot)[2]) { down_norms_finalize(st, init, tot); });
+    grid_sum_finalize<2>(acc, partials, counter, [=](const double(&tot)[2]) { down_norms_finalize(st, init, tot, dc); });
 }
 
 // Fine level, whole up leg in ONE launch, staged like k_down5: x += P e, one EXACT black/red sweep and
@@ -526,25 +551,29 @@ static_assert(kUpH == 2 * kDnWarps && kUpTX + 2 * kUpF == kDnW, "one coarse bloc
 
 __global__ void __launch_bounds__(kDnThreads, 2)
 k_up5(Fine5 v, const double *__restrict__ b, const double *__restrict__ xin, double *__restrict__ xout, Weights w,
-      const double *__restrict__ e, int nzc, int nxc, PcgState *st, int init, double *partials, unsigned int *counter)
+      const double *__restrict__ e, int nzc, int nxc, int wlo, int whi, PcgState *st, int init, double *partials,
+      unsigned int *counter, Dist dc)
 {
     if (stopped(st)) return;
     constexpr int W = kDnW, H = kUpH, F = kUpF, TZ = kUpTZ, TX = kUpTX;
     LCL_DYNAMIC_SMEM(double, smem);
     double *sb = smem, *stx = smem + H * W, *stz = smem + 2 * H * W, *sx = smem + 3 * H * W;
-    const int nz = v.nz, nx = v.nx;
-    const int tiles_x = (nx + TX - 1) / TX, tiles_z = (nz + TZ - 1) / TZ;
+    // strip: own rows [zlo, zhi), held rows [rlo, rhi); coarse blocks whose weights, coarse values and fine
+    // rows this rank holds: [blo, bhi)
+    const int nz = v.nz, nx = v.nx, zlo = v.zlo, zhi = v.zhi, rlo = read_lo(zlo), rhi = read_hi(zhi, nz);
+    const int blo = wlo > ((rlo + 1) >> 1) ? wlo : ((rlo + 1) >> 1), bhi = whi < ((rhi + 1) >> 1) ? whi : ((rhi + 1) >> 1);
+    const int tiles_x = (nx + TX - 1) / TX, tiles_z = (zhi - zlo + TZ - 1) / TZ;
     const int lane = threadIdx.x & 31, wy = threadIdx.x >> 5;
     double acc[2] = {0.0, 0.0};
     for (long long t = blockIdx.x; t < (long long)tiles_x * tiles_z; t += gridDim.x) {
-        const int z0 = (int)(t / tiles_x) * TZ, x0 = (int)(t % tiles_x) * TX;
+        const int z0 = zlo + (int)(t / tiles_x) * TZ, x0 = (int)(t % tiles_x) * TX;
         stage_tile5<F, H>(sb, stx, stz, v, b, z0, x0, wy, lane);
 #pragma unroll
         for (int br = wy; br < H / 2; br += kDnWarps) {
             // x + P e of the coarse block (br, lane) of the framed tile: rows 2br, 2br+1, columns 2lane, 2lane+1
             const int bz = (z0 >> 1) - 1 + br, bx = (x0 >> 1) - 1 + lane;
             double v00 = 0.0, v01 = 0.0, v10 = 0.0, v11 = 0.0;
-            if (bz >= 0 && bx >= 0 && bz < nzc && bx < nxc) {
+            if (bz >= blo && bx >= 0 && bz < bhi && bx < nxc) {
                 const size_t bk = (size_t)bz * nxc + bx;
                 const size_t i = (size_t)(2 * bz) * nx + 2 * bx;
                 const bool Xp = bx + 1 < nxc, Zp = bz + 1 < nzc;
@@ -574,7 +603,7 @@ k_up5(Fine5 v, const double *__restrict__ b, const double *__restrict__ xin, dou
             if (lx > TX) continue;
             const int z = z0 + lz, xx = x0 + lx, par = (lx + F) & 1;
             const int p = dn_pos(lz + F, lx + F), pl = p + (par ? -32 : 31), pr = p + (par ? -31 : 32);
-            if (z >= 0 && z < nz && xx >= 0 && xx < nx) {
+            if (z >= rlo && z < rhi && xx >= 0 && xx < nx) {
                 const double tl = stx[pl], tr = stx[p], td = stz[p - W], tu = stz[p];
                 double s = sb[p];
                 s += tl * sx[pl];
@@ -590,7 +619,7 @@ k_up5(Fine5 v, const double *__restrict__ b, const double *__restrict__ xin, dou
 #pragma unroll
         for (int lz = wy; lz < TZ; lz += kDnWarps) {
             const int z = z0 + lz, xe = x0 + 2 * lane;
-            if (lane >= TX / 2 || z >= nz || xe >= nx) continue;
+            if (lane >= TX / 2 || z >= zhi || xe >= nx) continue;
             const size_t i = (size_t)z * nx + xe;
             const int pe = dn_pos(lz + F, 2 * lane + F), po = pe + 32;
             const int r = lz & 1;                          // 0: the even cell is red, 1: the odd cell is red
@@ -617,7 +646,9 @@ k_up5(Fine5 v, const double *__restrict__ b, const double *__restrict__ xin, dou
         }
         __syncthreads();
     }
-    grid_sum_finalize<2>(acc, partials, counter, [=](const double(&tot)[2]) {
+    grid_sum_finalize<2>(acc, partials, counter, [=](const double(&part)[2]) {
+        double tot[1] = {part[0]};
+        dist_sum<1>(dc, tot);
         st->rz_new = tot[0];
         st->beta = init ? 0.0 : tot[0] / st->rz;
         st->rz = tot[0];
@@ -628,14 +659,14 @@ k_up5(Fine5 v, const double *__restrict__ b, const double *__restrict__ xin, dou
 // bc = P^T r : thread per coarse point gathers its 3x3 fine neighbourhood
 __global__ void __launch_bounds__(kBlock)
 k_restrict(Weights w, const double *__restrict__ r, int nz, int nx, double *__restrict__ bc, int nzc, int nxc,
-           const PcgState *st)
+           int czlo, int czhi, const PcgState *st)
 {
     if (stopped(st)) return;
-    const Tiles tiles(nzc, nxc);
+    const Tiles tiles(czlo, czhi, nxc);   // the coarse rows this rank owns (all of them on one GPU)
     for (long long t = blockIdx.x; t < tiles.ntiles; t += gridDim.x) {
         int Z, X;
         tiles.cell(t, Z, X);
-        if (Z >= nzc || X >= nxc) continue;
+        if (Z >= czhi || X >= nxc) continue;
         const int z = 2 * Z, x = 2 * X;
         const size_t b = (size_t)Z * nxc + X;
         const size_t i = (size_t)z * nx + x;
@@ -879,6 +910,7 @@ k_dot_norms(const double *__restrict__ b, const double *__restrict__ x, Fine5 v,
         acc[2] += bi * x[i];
     }
     grid_sum_finalize<3>(acc, partials, counter, [=](const double(&tot)[3]) {
+        st->dx = st->dx_part;   // a map this small is never striped: the strip's change is the map's
         st->rr = tot[0];
         st->rs = tot[1];
         if (init) { st->bb = tot[0]; st->bs = tot[1]; }
@@ -908,7 +940,7 @@ static int leg_grid(Solver &s, int tz, int tx)
         CUDA_CHECK(cudaFuncSetAttribute(k_smooth9<false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSm9SmemUp));
         s.down_configured = true;
     }
-    const long long tiles = (long long)div_up(s.nx, tx) * div_up(s.nz, tz);
+    const long long tiles = (long long)div_up(s.nx, tx) * div_up(s.zhi - s.zlo, tz);
     long long cap = (long long)s.num_sms * 2;
     if (cap > kMaxPartials) cap = kMaxPartials;
     return (int)(tiles < cap ? tiles : cap);
@@ -916,54 +948,76 @@ static int leg_grid(Solver &s, int tz, int tx)
 static int down_grid(Solver &s) { return leg_grid(s, kDnTZ, kDnTX); }
 static int up_grid(Solver &s) { return leg_grid(s, kUpTZ, kUpTX); }
 
+// persistent grid of the 9-point smoother over the rows a rank owns: two resident blocks per SM, each pipelining its tiles
+static int smooth_grid(const Solver &s, const Level &f)
+{
+    long long tiles = (long long)div_up(f.nx, kSmTX) * div_up(f.zhi - f.zlo, kSmTZ);
+    long long cap = (long long)s.num_sms * 2;
+    if (cap > kMaxPartials) cap = kMaxPartials;
+    return (int)(tiles < cap ? tiles : cap);
+}
+// coarse rows of level f's weights (and of the next level's vectors) this rank holds
+static int w_lo(const Level &f) { return f.striped ? read_lo(f.czlo) : 0; }
+static int w_hi(const Level &f, const Level &c) { return f.striped ? read_hi(f.czhi, c.nz) : c.nz; }
+// residual rows: a strip adds the row below its own (restriction of its first coarse row)
+static int res_lo(const Level &f) { return f.striped && f.zlo > 0 ? f.zlo - 1 : f.zlo; }
+
+static void broadcast1(Solver &s, double *p, int pitch, const int *cut, const PcgState *st)
+{
+    HaloSet hs;
+    hs.add(p);
+    row_broadcast(s, hs, pitch, cut, st);
+}
+static void exchange1(Solver &s, double *p, int pitch, const int *cut, int dlo, int dhi, const PcgState *st)
+{
+    HaloSet hs;
+    hs.add(p);
+    halo_exchange(s, hs, pitch, cut, dlo, dhi, st);
+}
+
 double bench_launch_cycle(Solver &s, const std::string &name)
 {
     const Fine5 v5 = s.view5();
     double *part = s.red + 16 * kMaxPartials;
     unsigned int *cnt = s.red_counters + 4;
-    const double n = (double)s.n;
-    auto tile_grid = [&](int nz, int nx) {
-        long long tiles = (long long)div_up(nx, kSmTX) * div_up(nz, kSmTZ);
-        long long cap = (long long)s.num_sms * 2;   // persistent: two resident blocks per SM, each pipelining its tiles
-        if (cap > kMaxPartials) cap = kMaxPartials;
-        return (int)(tiles < cap ? tiles : cap);
-    };
+    const double n = (double)s.own_cells();
     if (name == "up5" && s.levels.size() > 1 && s.levels[0].w.hw) {
-        Level &c = s.levels[1];
+        Level &f = s.levels[0], &c = s.levels[1];
         LAUNCH(k_up5, up_grid(s), kDnThreads, kUpSmem, s.stream, v5, (const double *)s.r, (const double *)s.z, s.q,
-               s.levels[0].w, (const double *)c.r, c.nz, c.nx, s.state, 0, part + 4 * kMaxPartials, cnt + 1);
-        return 40.0 * n + (8.0 + 64.0) * (double)c.n;   // x, b, tx, tz in; x out; coarse e + 8 weights
+               f.w, (const double *)c.r, c.nz, c.nx, w_lo(f), w_hi(f, c), s.state, 0, part + 4 * kMaxPartials, cnt + 1, s.dist);
+        return 40.0 * n + (8.0 + 64.0) * (double)(f.czhi - f.czlo) * c.nx;   // x, b, tx, tz in; x out; coarse e + 8 weights
     }
     if (name == "smooth9_l1" && s.levels.size() > 2) {
         Level &f = s.levels[1];
-        LAUNCH((k_smooth9<true, false, true>), tile_grid(f.nz, f.nx), kSmThreads, kSm9Smem, s.stream, f.view9(), (const double *)f.b,
-               (const double *)nullptr, f.x, s.nu_coarse, Weights{}, (const double *)nullptr, 0, 0,
+        LAUNCH((k_smooth9<true, false, true>), smooth_grid(s, f), kSmThreads, kSm9Smem, s.stream, f.view9(), (const double *)f.b,
+               (const double *)nullptr, f.x, s.nu_coarse, Weights{}, (const double *)nullptr, 0, 0, 0, 0,
                (const PcgState *)s.state);
-        return 56.0 * (double)f.n;   // b, C, E, N, NE, NW in; x out (couplings re-read from L1/L2 per sweep)
+        return 56.0 * (double)f.own_cells();   // b, C, E, N, NE, NW in; x out (couplings re-read from L1/L2 per sweep)
     }
     if (name == "down5" && s.levels.size() > 1 && s.levels[0].w.hw) {
-        Level &c = s.levels[1];
-        LAUNCH(k_down5, down_grid(s), kDnThreads, kDnSmem, s.stream, v5, s.levels[0].w, (const double *)s.r, s.z, c.b, c.nz,
-               c.nx, s.state, 0, part, cnt);
-        return 32.0 * n + (8.0 + 32.0) * (double)c.n;   // b, tx, tz in, x out; 4 weights in + coarse rhs out
+        Level &f = s.levels[0], &c = s.levels[1];
+        LAUNCH(k_down5, down_grid(s), kDnThreads, kDnSmem, s.stream, v5, f.w, (const double *)s.r, s.z, c.b, c.nz,
+               c.nx, f.czhi, s.state, 0, part, cnt, s.dist);
+        return 32.0 * n + (8.0 + 32.0) * (double)(f.czhi - f.czlo) * c.nx;   // b, tx, tz in, x out; 4 weights in + coarse rhs out
     }
     if (name == "smooth9_l1_up" && s.levels.size() > 2) {
         Level &f = s.levels[1], &c = s.levels[2];
-        LAUNCH((k_smooth9<false, true, false>), tile_grid(f.nz, f.nx), kSmThreads, kSm9SmemUp, s.stream, f.view9(), (const double *)f.b,
-               (const double *)f.x, f.r, s.nu_coarse, f.w, (const double *)c.r, c.nz, c.nx, (const PcgState *)s.state);
-        return 64.0 * (double)f.n + (8.0 + 64.0) * (double)c.n;
+        LAUNCH((k_smooth9<false, true, false>), smooth_grid(s, f), kSmThreads, kSm9SmemUp, s.stream, f.view9(), (const double *)f.b,
+               (const double *)f.x, f.r, s.nu_coarse, f.w, (const double *)c.r, c.nz, c.nx, w_lo(f), w_hi(f, c),
+               (const PcgState *)s.state);
+        return 64.0 * (double)f.own_cells() + (8.0 + 64.0) * (double)(f.czhi - f.czlo) * c.nx;
     }
     if (name == "residual9_l1" && s.levels.size() > 2) {
         Level &f = s.levels[1];
-        LAUNCH(k_residual9, grid_for(s, f.nz, f.nx, 8), kBlock, 0, s.stream, f.view9(), (const double *)f.b,
-               (const double *)f.x, f.r, s.state);
-        return 64.0 * (double)f.n;   // b, x, S, E, N, NE, NW in; r out
+        LAUNCH(k_residual9, grid_for(s, f.zhi - res_lo(f), f.nx, 8), kBlock, 0, s.stream, f.view9(), (const double *)f.b,
+               (const double *)f.x, f.r, res_lo(f), f.zhi, s.state);
+        return 64.0 * (double)f.own_cells();   // b, x, S, E, N, NE, NW in; r out
     }
     if (name == "restrict1" && s.levels.size() > 2) {
         Level &f = s.levels[1], &c = s.levels[2];
-        LAUNCH(k_restrict, grid_for(s, c.nz, c.nx, 8), kBlock, 0, s.stream, f.w, (const double *)f.r, f.nz, f.nx,
-               c.b, c.nz, c.nx, s.state);
-        return 8.0 * (double)f.n + 72.0 * (double)c.n;
+        LAUNCH(k_restrict, grid_for(s, f.czhi - f.czlo, c.nx, 8), kBlock, 0, s.stream, f.w, (const double *)f.r, f.nz, f.nx,
+               c.b, c.nz, c.nx, f.czlo, f.czhi, s.state);
+        return 8.0 * (double)f.own_cells() + 72.0 * (double)(f.czhi - f.czlo) * c.nx;
     }
     if (name == "vcycle") {
         mg_vcycle(s, s.r, s.z, s.q, s.state, false);
@@ -972,20 +1026,21 @@ double bench_launch_cycle(Solver &s, const std::string &name)
     return -1.0;
 }
 
+// One cycle.  On a striped level every kernel walks the rank's own rows; what it reads beyond them are ghost
+// rows that the producing step has pushed to the neighbours (halo_exchange, peer stores + a flag, no NCCL):
+//   fine level   r (4 rows below / 2 above: the down leg recomputes its frame), the down leg's x (2 / 2), z (1 / 1)
+//   9-point level l   x and b after the down smoother (2 / 2: residual of the row below the strip, frame of the up
+//                     smoother), the level's result after the up smoother (2 / 2: prolongation one level up, or
+//                     the starting guess of a second visit)
+// The right-hand side of the first whole level is assembled from all ranks' rows (row_broadcast); from there
+// down every rank cycles the same small problem redundantly, and its result needs no exchange on the way up.
 void mg_vcycle(Solver &s, const double *r, double *ztmp, double *zout, PcgState *st, bool init_flag)
 {
     const int init = init_flag ? 1 : 0;
     const Fine5 v5 = s.view5();
-    const int g0 = grid_for(s, s.nz, s.nx, 8);
     double *part = s.red + 16 * kMaxPartials;   // slots 16.. belong to the cycle
     unsigned int *cnt = s.red_counters + 4;
     const size_t nlev = s.levels.size();
-    auto tile_grid = [&](int nz, int nx) {
-        long long tiles = (long long)div_up(nx, kSmTX) * div_up(nz, kSmTZ);
-        long long cap = (long long)s.num_sms * 2;   // persistent: two resident blocks per SM, each pipelining its tiles
-        if (cap > kMaxPartials) cap = kMaxPartials;
-        return (int)(tiles < cap ? tiles : cap);
-    };
 
     if (s.levels[0].w.hw == nullptr) {   // map small enough for the dense solve alone
         Level &c = s.levels[1];
@@ -999,9 +1054,14 @@ void mg_vcycle(Solver &s, const double *r, double *ztmp, double *zout, PcgState 
     // residual it held has been restricted by then).  Fine level: ztmp after the down leg, zout final;
     // zout doubles as the fine residual buffer in between.
     {   // whole fine down leg: smooth, residual, restriction
-        Level &c = s.levels[1];
-        LAUNCH_DEP(k_down5, down_grid(s), kDnThreads, kDnSmem, s.stream, v5, s.levels[0].w, r, ztmp, c.b, c.nz, c.nx, st, init,
-               part, cnt);
+        Level &f = s.levels[0], &c = s.levels[1];
+        if (f.striped) exchange1(s, const_cast<double *>(r), f.nx, f.cut, 4, 2, st);
+        LAUNCH_DEP(k_down5, down_grid(s), kDnThreads, kDnSmem, s.stream, v5, f.w, r, ztmp, c.b, c.nz, c.nx, f.czhi, st, init,
+               part, cnt, s.dist);
+        if (f.striped) {
+            exchange1(s, ztmp, f.nx, f.cut, 2, 2, st);
+            if (!c.striped) broadcast1(s, c.b, c.nx, f.ccut, st);
+        }
     }
     // Levels >= 1: cycle(l) solves level l approximately for the right-hand side in .b, result in .r.
     // Levels in [w_lo, w_hi] are visited twice (second time from the first result): a W-cycle
@@ -1023,29 +1083,38 @@ void mg_vcycle(Solver &s, const double *r, double *ztmp, double *zout, PcgState 
         Level &c = s.levels[l + 1];
         const int nu = l == 1 ? s.nu_coarse : s.nu_deep;
         if (zero_init)
-            LAUNCH_DEP((k_smooth9<true, false, true>), tile_grid(f.nz, f.nx), kSmThreads, kSm9Smem, s.stream, f.view9(),
-                   (const double *)f.b, (const double *)nullptr, f.x, nu, now, (const double *)nullptr, 0, 0,
+            LAUNCH_DEP((k_smooth9<true, false, true>), smooth_grid(s, f), kSmThreads, kSm9Smem, s.stream, f.view9(),
+                   (const double *)f.b, (const double *)nullptr, f.x, nu, now, (const double *)nullptr, 0, 0, 0, 0,
                    (const PcgState *)st);
         else
-            LAUNCH_DEP((k_smooth9<false, false, true>), tile_grid(f.nz, f.nx), kSmThreads, kSm9Smem, s.stream, f.view9(),
-                   (const double *)f.b, (const double *)f.r, f.x, nu, now, (const double *)nullptr, 0, 0,
+            LAUNCH_DEP((k_smooth9<false, false, true>), smooth_grid(s, f), kSmThreads, kSm9Smem, s.stream, f.view9(),
+                   (const double *)f.b, (const double *)f.r, f.x, nu, now, (const double *)nullptr, 0, 0, 0, 0,
                    (const PcgState *)st);
-        LAUNCH_DEP(k_residual9, grid_for(s, f.nz, f.nx, 8), kBlock, 0, s.stream, f.view9(), (const double *)f.b,
-               (const double *)f.x, f.r, st);
-        LAUNCH_DEP(k_restrict, grid_for(s, c.nz, c.nx, 8), kBlock, 0, s.stream, f.w, (const double *)f.r, f.nz, f.nx,
-               c.b, c.nz, c.nx, st);
+        if (f.striped) {   // b rides along: the residual of the row below the strip reads it
+            HaloSet hs;
+            hs.add(f.x);
+            hs.add(f.b);
+            halo_exchange(s, hs, f.nx, f.cut, 2, 2, st);
+        }
+        LAUNCH_DEP(k_residual9, grid_for(s, f.zhi - res_lo(f), f.nx, 8), kBlock, 0, s.stream, f.view9(), (const double *)f.b,
+               (const double *)f.x, f.r, res_lo(f), f.zhi, st);
+        LAUNCH_DEP(k_restrict, grid_for(s, f.czhi - f.czlo, c.nx, 8), kBlock, 0, s.stream, f.w, (const double *)f.r, f.nz, f.nx,
+               c.b, c.nz, c.nx, f.czlo, f.czhi, st);
+        if (f.striped && !c.striped) broadcast1(s, c.b, c.nx, f.ccut, st);
         cycle(l + 1, true);
         if ((int)(l + 1) >= s.w_lo && (int)(l + 1) <= s.w_hi && l + 1 < nlev - 1) cycle(l + 1, false);
-        LAUNCH_DEP((k_smooth9<false, true, false>), tile_grid(f.nz, f.nx), kSmThreads, kSm9SmemUp, s.stream, f.view9(),
-               (const double *)f.b, (const double *)f.x, f.r, nu, f.w, (const double *)c.r, c.nz, c.nx,
+        LAUNCH_DEP((k_smooth9<false, true, false>), smooth_grid(s, f), kSmThreads, kSm9SmemUp, s.stream, f.view9(),
+               (const double *)f.b, (const double *)f.x, f.r, nu, f.w, (const double *)c.r, c.nz, c.nx, w_lo(f), w_hi(f, c),
                (const PcgState *)st);
+        if (f.striped) exchange1(s, f.r, f.nx, f.cut, 2, 2, st);
     };
     cycle(1, true);
     if (1 >= s.w_lo && 1 <= s.w_hi && nlev > 2) cycle(1, false);
     {
-        Level &c = s.levels[1];
-        LAUNCH_DEP(k_up5, up_grid(s), kDnThreads, kUpSmem, s.stream, v5, r, (const double *)ztmp, zout, s.levels[0].w,
-               (const double *)c.r, c.nz, c.nx, st, init, part + 4 * kMaxPartials, cnt + 1);
+        Level &f = s.levels[0], &c = s.levels[1];
+        LAUNCH_DEP(k_up5, up_grid(s), kDnThreads, kUpSmem, s.stream, v5, r, (const double *)ztmp, zout, f.w,
+               (const double *)c.r, c.nz, c.nx, w_lo(f), w_hi(f, c), st, init, part + 4 * kMaxPartials, cnt + 1, s.dist);
+        if (f.striped) exchange1(s, zout, f.nx, f.cut, 1, 1, st);
     }
 }
 

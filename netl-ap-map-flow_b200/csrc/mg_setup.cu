@@ -34,14 +34,14 @@ __device__ __forceinline__ double neg(double g) { return g < 0.0 ? g : 0.0; }
 // ------------------------------------------------------------------------------ edge weights
 template <class Op>
 __global__ void __launch_bounds__(kBlock)
-k_weights_edges(Op A, int nzc, int nxc, Weights w)
+k_weights_edges(Op A, int nzc, int nxc, Weights w, int czlo, int czhi)
 {
     const int nz = A.nz(), nx = A.nx();
-    const Tiles tiles(nzc, nxc);
+    const Tiles tiles(czlo, czhi, nxc);
     for (long long t = blockIdx.x; t < tiles.ntiles; t += gridDim.x) {
         int Z, X;
         tiles.cell(t, Z, X);
-        if (Z >= nzc || X >= nxc) continue;
+        if (Z >= czhi || X >= nxc) continue;
         const size_t b = (size_t)Z * nxc + X;
         double hw = 0.0, he = 0.0, vs = 0.0, vn = 0.0, th = 0.0, tv = 0.0;
         {   // h-edge point (2Z, 2X+1)
@@ -73,14 +73,14 @@ k_weights_edges(Op A, int nzc, int nxc, Weights w)
 // ---------------------------------------------------------------------------- centre weights
 template <class Op>
 __global__ void __launch_bounds__(kBlock)
-k_weights_centres(Op A, int nzc, int nxc, Weights w)
+k_weights_centres(Op A, int nzc, int nxc, Weights w, int czlo, int czhi)
 {
     const int nz = A.nz(), nx = A.nx();
-    const Tiles tiles(nzc, nxc);
+    const Tiles tiles(czlo, czhi, nxc);
     for (long long t = blockIdx.x; t < tiles.ntiles; t += gridDim.x) {
         int Z, X;
         tiles.cell(t, Z, X);
-        if (Z >= nzc || X >= nxc) continue;
+        if (Z >= czhi || X >= nxc) continue;
         const size_t b = (size_t)Z * nxc + X;
         double c[4] = {0.0, 0.0, 0.0, 0.0};   // sw, se, nw, ne
         double tc = 0.0;
@@ -136,14 +136,14 @@ k_weights_centres(Op A, int nzc, int nxc, Weights w)
 template <class Op>
 __global__ void __launch_bounds__(kBlock)
 k_galerkin(Op A, int nzc, int nxc, Weights w, double *__restrict__ Sc, double *__restrict__ Ec,
-           double *__restrict__ Nc, double *__restrict__ NEc, double *__restrict__ NWc)
+           double *__restrict__ Nc, double *__restrict__ NEc, double *__restrict__ NWc, int czlo, int czhi)
 {
     const int nz = A.nz(), nx = A.nx();
-    const Tiles tiles(nzc, nxc);
+    const Tiles tiles(czlo, czhi, nxc);
     for (long long t = blockIdx.x; t < tiles.ntiles; t += gridDim.x) {
         int Z, X;
         tiles.cell(t, Z, X);
-        if (Z >= nzc || X >= nxc) continue;
+        if (Z >= czhi || X >= nxc) continue;
         double acc[4] = {0.0, 0.0, 0.0, 0.0};
         double sabs = 0.0;
         constexpr int jz[4] = {0, 1, 1, 1}, jx[4] = {1, 0, 1, -1};   // E, N, NE, NW of (Z, X)
@@ -197,11 +197,11 @@ __global__ void __launch_bounds__(kBlock)
 k_coarse_diag(Coarse9 v, double *__restrict__ C)
 {
     const C9 A{v};
-    const Tiles tiles(v.nz, v.nx);
+    const Tiles tiles(v.zlo, v.zhi, v.nx);
     for (long long t = blockIdx.x; t < tiles.ntiles; t += gridDim.x) {
         int z, x;
         tiles.cell(t, z, x);
-        if (z >= v.nz || x >= v.nx) continue;
+        if (z >= v.zhi || x >= v.nx) continue;
         double s = A.S(z, x);
 #pragma unroll
         for (int dz = -1; dz <= 1; dz++)
@@ -262,77 +262,124 @@ __global__ void k_coarse_inverse(Coarse9 v, double *__restrict__ inv, double *__
 // ------------------------------------------------------------------------------------ host side
 constexpr int kCoarsestCells = 48;   // dense inverse in shared memory: 48*96*8 = 36 KB
 
-static void alloc_d(double **p, size_t count) { CUDA_CHECK(cudaMalloc((void **)p, (count ? count : 1) * sizeof(double))); }
-
-void mg_allocate(Solver &s)
+// Level sizes, and for a striped solve (world > 1) which levels are striped and where the strips are cut.
+// Levels 0 .. gather_level-1 are striped, gather_level and everything below it is held whole by every rank
+// and cycled redundantly: a level of a million cells is a handful of microseconds per kernel, launch latency
+// that no split shortens, while every striped level costs two neighbour synchronisations per visit.  Strip
+// boundaries are multiples of 16 rows on every striped 9-point level (the hybrid smoother's tiles must not
+// straddle a cut: Jacobi between tiles, Gauss-Seidel inside, exactly the single-GPU iteration) and of two
+// rows on the fine level (red/black parity, 2x2 coarse blocks).
+void mg_plan(Solver &s)
 {
     s.levels.clear();
     Level l0;
     l0.nz = s.nz; l0.nx = s.nx; l0.n = s.n;
     s.levels.push_back(l0);
     while ((long long)s.levels.back().nz * s.levels.back().nx > kCoarsestCells) {
-        Level &f = s.levels.back();
+        const Level &f = s.levels.back();
         Level c;
         c.nz = (f.nz + 1) / 2; c.nx = (f.nx + 1) / 2; c.n = (size_t)c.nz * c.nx;
-        double **wp[11] = {&f.w.hw, &f.w.he, &f.w.vs, &f.w.vn, &f.w.csw, &f.w.cse, &f.w.cnw, &f.w.cne,
-                           &f.w.th, &f.w.tv, &f.w.tc};
-        for (auto p : wp) alloc_d(p, c.n);
-        double **cp[9] = {&c.C, &c.S, &c.E, &c.N, &c.NE, &c.NW, &c.x, &c.b, &c.r};
-        for (auto p : cp) alloc_d(p, c.n);
         s.levels.push_back(c);
     }
-    if (s.levels.size() == 1) {
-        // tiny map: still give it one coarse "level" equal to itself?  No: the cycle handles a
-        // single-level hierarchy by smoothing + dense solve of a 9-point copy of the fine operator.
+    const bool single = s.levels.size() == 1;   // tiny map: one dense "level" equal to the fine grid
+    if (single) {
         Level c;
         c.nz = s.nz; c.nx = s.nx; c.n = s.n;
-        double **cp[9] = {&c.C, &c.S, &c.E, &c.N, &c.NE, &c.NW, &c.x, &c.b, &c.r};
-        for (auto p : cp) alloc_d(p, c.n);
         s.levels.push_back(c);
-        s.levels[0].w = Weights{};   // marks "identity transfer"
     }
-    s.coarse_n = (int)s.levels.back().n;
-    alloc_d(&s.coarse_inv, (size_t)s.coarse_n * s.coarse_n);
-    alloc_d(&s.coarse_scale, s.coarse_n);
+    const int nlev = (int)s.levels.size();
     // the levels one block cycles in one launch (k_tail_cycle): the first coarse level with at most
     // kTailCells cells and everything below it, if that is more than the dense level alone
     s.tail_top = -1;
-    s.tail = TailArgs{};
-    if (s.levels[0].w.hw && !getenv("APM_LCL_NO_TAIL")) {
-        const size_t nlev = s.levels.size();
-        size_t top = 1;
+    s.tail_smem = 0;
+    if (!single && !getenv("APM_LCL_NO_TAIL")) {
+        int top = 1;
         while (top < nlev && s.levels[top].n > (size_t)kTailCells) top++;
         size_t framed = 0, plain = 0;
-        for (size_t l = top; l < nlev; l++) {
+        for (int l = top; l < nlev; l++) {
             framed += (size_t)(s.levels[l].nz + 2) * (s.levels[l].nx + 2);
             plain += s.levels[l].n;
         }
-        s.tail_smem = (2 * framed + plain) * sizeof(double);
-        if (top + 1 < nlev && nlev - top <= (size_t)kTailMaxLevels && s.coarse_n <= 64 && s.tail_smem <= kTailMaxSmem) {
-            s.tail_top = (int)top;
-            s.tail.nlev = (int)(nlev - top);
-            for (size_t l = top; l < nlev; l++) {
-                const Level &L = s.levels[l];
-                s.tail.lv[l - top] = TailLevel{L.view9(), L.w, L.x, L.b, L.r};
-            }
-            s.tail.inv = s.coarse_inv;
-            s.tail.scale = s.coarse_scale;
+        const size_t smem = (2 * framed + plain) * sizeof(double);
+        if (top + 1 < nlev && nlev - top <= kTailMaxLevels && (long long)s.levels.back().n <= 64 && smem <= kTailMaxSmem) {
+            s.tail_top = top;
+            s.tail_smem = smem;
         }
     }
+    // ---- strips
+    int lg = 0;
+    if (s.world > 1 && !single) {
+        size_t min_cells = (size_t)1 << 20;
+        if (const char *e = getenv("APM_LCL_STRIPE_MIN_CELLS")) min_cells = (size_t)atoll(e);
+        const int cap = s.tail_top > 0 ? s.tail_top : nlev - 1;   // the tail and the dense level are never striped
+        while (lg < cap && s.levels[lg].n > min_cells) lg++;
+    }
+    int cut0[kMaxRanks + 1] = {0};
+    for (; lg > 0; lg--) {
+        const int align = lg >= 2 ? 16 << (lg - 1) : 2;
+        bool ok = true;
+        for (int k = 0; k <= s.world; k++) {
+            long long c = ((long long)k * s.nz / s.world + align / 2) / align * align;
+            cut0[k] = k == s.world ? s.nz : (int)c;
+        }
+        for (int k = 0; k < s.world; k++) ok &= cut0[k + 1] - cut0[k] >= (align > 32 ? align : 32);
+        if (ok) break;
+    }
+    s.gather_level = lg;
+    for (int l = 0; l < nlev; l++) {
+        Level &L = s.levels[l];
+        L.striped = l < lg;
+        for (int k = 0; k <= s.world; k++) {
+            L.cut[k] = L.striped ? (k == s.world ? L.nz : cut0[k] >> l) : (k == 0 ? 0 : L.nz);
+            const int cnz = l + 1 < nlev ? s.levels[l + 1].nz : 0;
+            L.ccut[k] = L.striped ? (k == s.world ? cnz : cut0[k] >> (l + 1)) : (k == 0 ? 0 : cnz);
+        }
+        if (L.striped) {
+            L.zlo = L.cut[s.rank]; L.zhi = L.cut[s.rank + 1];
+            L.czlo = L.ccut[s.rank]; L.czhi = L.ccut[s.rank + 1];
+        } else {
+            L.zlo = 0; L.zhi = L.nz;
+            L.czlo = 0; L.czhi = l + 1 < nlev ? s.levels[l + 1].nz : 0;
+            // a whole level is "cut" so that rank 0 owns everything: the exchange helpers are never called for it
+            for (int k = 1; k <= s.world; k++) { L.cut[k] = L.nz; L.ccut[k] = L.czhi; }
+        }
+    }
+    s.zlo = s.levels[0].zlo;
+    s.zhi = s.levels[0].zhi;
 }
 
-void mg_free(Solver &s)
+void mg_allocate(Solver &s, Arena &a)
 {
-    for (auto &l : s.levels) {
-        double *ptrs[20] = {l.C, l.S, l.E, l.N, l.NE, l.NW, l.x, l.b, l.r, l.w.hw, l.w.he, l.w.vs, l.w.vn,
-                            l.w.csw, l.w.cse, l.w.cnw, l.w.cne, l.w.th, l.w.tv, l.w.tc};
-        for (double *p : ptrs)
-            if (p) cudaFree(p);
+    const int nlev = (int)s.levels.size();
+    const bool single = nlev == 2 && s.levels[1].n == s.levels[0].n && s.levels[0].n <= (size_t)kCoarsestCells;
+    for (int l = 0; l < nlev; l++) {
+        Level &L = s.levels[l];
+        if (l > 0) {
+            double **cp[9] = {&L.C, &L.S, &L.E, &L.N, &L.NE, &L.NW, &L.x, &L.b, &L.r};
+            for (auto p : cp) *p = a.take_rows(L.nx, L.nz, L.striped, L.cut, s.rank, s.world);
+        }
+        if (l + 1 < nlev && !single) {
+            const Level &c = s.levels[l + 1];
+            double **wp[11] = {&L.w.hw, &L.w.he, &L.w.vs, &L.w.vn, &L.w.csw, &L.w.cse, &L.w.cnw, &L.w.cne,
+                               &L.w.th, &L.w.tv, &L.w.tc};
+            for (auto p : wp) *p = a.take_rows(c.nx, c.nz, L.striped, L.ccut, s.rank, s.world);
+        } else {
+            L.w = Weights{};   // the coarsest level; on the fine level of a tiny map it marks "identity transfer"
+        }
     }
-    s.levels.clear();
-    if (s.coarse_inv) cudaFree(s.coarse_inv);
-    if (s.coarse_scale) cudaFree(s.coarse_scale);
-    s.coarse_inv = s.coarse_scale = nullptr;
+    s.coarse_n = (int)s.levels.back().n;
+    s.coarse_inv = a.take((size_t)s.coarse_n * s.coarse_n);
+    s.coarse_scale = a.take(s.coarse_n);
+    s.tail = TailArgs{};
+    if (s.tail_top > 0) {
+        s.tail.nlev = nlev - s.tail_top;
+        for (int l = s.tail_top; l < nlev; l++) {
+            const Level &L = s.levels[l];
+            s.tail.lv[l - s.tail_top] = TailLevel{L.view9(), L.w, L.x, L.b, L.r};
+        }
+        s.tail.inv = s.coarse_inv;
+        s.tail.scale = s.coarse_scale;
+    }
 }
 
 // copy of the fine 5-point operator as a 9-point one (only for maps with <= kCoarsestCells cells)
@@ -351,14 +398,39 @@ __global__ void k_fine_as_coarse(Fine5 v, double *C, double *S, double *E, doubl
     }
 }
 
+// One coarsening step.  On a striped level every rank computes the weights and the Galerkin rows of its own
+// coarse rows [czlo, czhi); what the next kernel reads beyond them arrives by halo exchange (weights: two
+// coarse rows either side; operators: the full ghost depth, they are read by every kernel of the cycle).
+// The first level held whole by every rank gets its operator rows from all ranks (row_broadcast).
 template <class Op>
 static void build_next(Solver &s, const Op &A, Level &f, Level &c)
 {
-    const int grid = grid_for(s, c.nz, c.nx, 8);
-    LAUNCH((k_weights_edges<Op>), grid, kBlock, 0, s.stream, A, c.nz, c.nx, f.w);
-    LAUNCH((k_weights_centres<Op>), grid, kBlock, 0, s.stream, A, c.nz, c.nx, f.w);
-    LAUNCH((k_galerkin<Op>), grid, kBlock, 0, s.stream, A, c.nz, c.nx, f.w, c.S, c.E, c.N, c.NE, c.NW);
-    LAUNCH(k_coarse_diag, grid, kBlock, 0, s.stream, c.view9(), c.C);
+    const int grid = grid_for(s, f.czhi - f.czlo, c.nx, 8);
+    LAUNCH((k_weights_edges<Op>), grid, kBlock, 0, s.stream, A, c.nz, c.nx, f.w, f.czlo, f.czhi);
+    if (f.striped) {
+        HaloSet hs;
+        for (double *p : {f.w.hw, f.w.he, f.w.vs, f.w.vn, f.w.th, f.w.tv}) hs.add(p);
+        halo_exchange(s, hs, c.nx, f.ccut, 2, 2, nullptr);
+    }
+    LAUNCH((k_weights_centres<Op>), grid, kBlock, 0, s.stream, A, c.nz, c.nx, f.w, f.czlo, f.czhi);
+    if (f.striped) {
+        HaloSet hs;
+        for (double *p : {f.w.csw, f.w.cse, f.w.cnw, f.w.cne, f.w.tc}) hs.add(p);
+        halo_exchange(s, hs, c.nx, f.ccut, 2, 2, nullptr);
+    }
+    LAUNCH((k_galerkin<Op>), grid, kBlock, 0, s.stream, A, c.nz, c.nx, f.w, c.S, c.E, c.N, c.NE, c.NW, f.czlo, f.czhi);
+    if (f.striped) {
+        HaloSet hs;
+        for (double *p : {c.S, c.E, c.N, c.NE, c.NW}) hs.add(p);
+        if (c.striped) halo_exchange(s, hs, c.nx, c.cut, kHalo, kHalo, nullptr);
+        else row_broadcast(s, hs, c.nx, f.ccut, nullptr);
+    }
+    LAUNCH(k_coarse_diag, grid_for(s, c.zhi - c.zlo, c.nx, 8), kBlock, 0, s.stream, c.view9(), c.C);
+    if (c.striped) {
+        HaloSet hs;
+        hs.add(c.C);
+        halo_exchange(s, hs, c.nx, c.cut, kHalo, kHalo, nullptr);
+    }
 }
 
 void mg_setup(Solver &s)

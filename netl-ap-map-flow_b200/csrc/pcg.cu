@@ -26,11 +26,11 @@ __global__ void __launch_bounds__(kBlock)
 k_init_rhs(Fine5 v, BoundaryValues bv, double *__restrict__ r, double *__restrict__ x)
 {
     const int nz = v.nz, nx = v.nx;
-    const Tiles tiles(nz, nx);
+    const Tiles tiles(v.zlo, v.zhi, nx);
     for (long long t = blockIdx.x; t < tiles.ntiles; t += gridDim.x) {
         int z, xx;
         tiles.cell(t, z, xx);
-        if (z >= nz || xx >= nx) continue;
+        if (z >= v.zhi || xx >= nx) continue;
         const size_t i = (size_t)z * nx + xx;
         double b = 0.0;
         if (xx == 0) b += v.txl[z] * bv.left;
@@ -45,17 +45,17 @@ k_init_rhs(Fine5 v, BoundaryValues bv, double *__restrict__ r, double *__restric
 // q = A d and d.q;  alpha = rz / d.q
 __global__ void __launch_bounds__(kBlock)
 k_spmv5(Fine5 v, const double *__restrict__ d, double *__restrict__ q, PcgState *st, double *partials,
-        unsigned int *counter)
+        unsigned int *counter, Dist dc)
 {
     if (stopped(st)) return;
     const F5 A{v};
     const int nz = v.nz, nx = v.nx;
-    const Tiles tiles(nz, nx);
+    const Tiles tiles(v.zlo, v.zhi, nx);
     double acc[1] = {0.0};
     for (long long t = blockIdx.x; t < tiles.ntiles; t += gridDim.x) {
         int z, xx;
         tiles.cell(t, z, xx);
-        if (z >= nz || xx >= nx) continue;
+        if (z >= v.zhi || xx >= nx) continue;
         const size_t i = (size_t)z * nx + xx;
         const double tl = A.left(z, xx), tr = A.right(z, xx), td = A.down(z, xx), tu = A.up(z, xx);
         const double di = d[i];
@@ -67,7 +67,9 @@ k_spmv5(Fine5 v, const double *__restrict__ d, double *__restrict__ q, PcgState 
         q[i] = s;
         acc[0] += di * s;
     }
-    grid_sum_finalize<1>(acc, partials, counter, [=](const double(&tot)[1]) {
+    grid_sum_finalize<1>(acc, partials, counter, [=](const double(&part)[1]) {
+        double tot[1] = {part[0]};
+        dist_sum<1>(dc, tot);
         st->dq = tot[0];
         if (!(tot[0] > 0.0) || !(st->rz == st->rz)) {
             // curvature lost to rounding: harmless once the residual tests have passed (floating
@@ -95,10 +97,12 @@ k_update(double *__restrict__ x, double *__restrict__ r, const double *__restric
         r[i] -= alpha * q[i];
         dmax = fmax(dmax, fabs(di));
     }
+    // this strip's largest change; the ranks' values meet in the gather of the down leg (mg_cycle.cu), which
+    // is where the stopping rule looks at them
     grid_max_finalize(dmax, partials, counter, [=](double m) {
         st->dx_prev2 = st->dx_prev;
         st->dx_prev = st->dx;
-        st->dx = fabs(alpha) * m;
+        st->dx_part = fabs(alpha) * m;
     });
 }
 
@@ -115,16 +119,16 @@ k_direction(double *__restrict__ d, const double *__restrict__ z, size_t n, cons
 // true residual r = b - A x with both norms (verification after the recurrence says "converged")
 __global__ void __launch_bounds__(kBlock)
 k_true_residual(Fine5 v, BoundaryValues bv, const double *__restrict__ x, double *__restrict__ r, double *out,
-                double *partials, unsigned int *counter)
+                double *partials, unsigned int *counter, Dist dc)
 {
     const F5 A{v};
     const int nz = v.nz, nx = v.nx;
-    const Tiles tiles(nz, nx);
+    const Tiles tiles(v.zlo, v.zhi, nx);
     double acc[2] = {0.0, 0.0};
     for (long long t = blockIdx.x; t < tiles.ntiles; t += gridDim.x) {
         int z, xx;
         tiles.cell(t, z, xx);
-        if (z >= nz || xx >= nx) continue;
+        if (z >= v.zhi || xx >= nx) continue;
         const size_t i = (size_t)z * nx + xx;
         const double tl = A.left(z, xx), tr = A.right(z, xx), td = A.down(z, xx), tu = A.up(z, xx);
         const double dg = (tl + tr) + (td + tu);
@@ -137,28 +141,42 @@ k_true_residual(Fine5 v, BoundaryValues bv, const double *__restrict__ x, double
         acc[0] += s * s;
         acc[1] += s * s / dg;
     }
-    grid_sum_finalize<2>(acc, partials, counter, [=](const double(&tot)[2]) {
+    grid_sum_finalize<2>(acc, partials, counter, [=](const double(&part)[2]) {
+        double tot[2] = {part[0], part[1]};
+        dist_sum<2>(dc, tot);
         out[0] = tot[0];
         out[1] = tot[1];
     });
 }
 
+// d = z + beta d runs one row beyond the strip either side: z arrives there by halo exchange (end of the cycle),
+// so d's ghost rows (read by the next spmv) need no exchange of their own
+static void launch_direction(Solver &s, const double *z, int init, bool dep)
+{
+    const int lo = s.levels[0].striped && s.zlo > 0 ? s.zlo - 1 : s.zlo;
+    const int hi = s.levels[0].striped && s.zhi < s.nz ? s.zhi + 1 : s.zhi;
+    const size_t off = (size_t)lo * s.nx, cnt = (size_t)(hi - lo) * s.nx;
+    const int g1 = s.num_sms * 8;
+    if (dep) LAUNCH_DEP(k_direction, g1, 256, 0, s.stream, s.d + off, z + off, cnt, (const PcgState *)s.state, init);
+    else LAUNCH(k_direction, g1, 256, 0, s.stream, s.d + off, z + off, cnt, (const PcgState *)s.state, init);
+}
+
 double bench_launch_pcg(Solver &s, const std::string &name)
 {
     const Fine5 v5 = s.view5();
-    const int g0 = grid_for(s, s.nz, s.nx, 8), g1 = s.num_sms * 8;
-    const double n = (double)s.n;
+    const int g0 = grid_for(s, s.zhi - s.zlo, s.nx, 8), g1 = s.num_sms * 8;
+    const double n = (double)s.own_cells();
     if (name == "spmv") {
-        LAUNCH(k_spmv5, g0, kBlock, 0, s.stream, v5, (const double *)s.d, s.q, s.state, s.red, s.red_counters);
+        LAUNCH(k_spmv5, g0, kBlock, 0, s.stream, v5, (const double *)s.d, s.q, s.state, s.red, s.red_counters, s.dist);
         return 32.0 * n;
     }
     if (name == "update") {
-        LAUNCH(k_update, g1, 256, 0, s.stream, s.x, s.r, (const double *)s.d, (const double *)s.q, s.n, s.state,
-               s.red + 4 * kMaxPartials, s.red_counters + 5);
+        LAUNCH(k_update, g1, 256, 0, s.stream, s.own(s.x), s.own(s.r), (const double *)s.own(s.d), (const double *)s.own(s.q),
+               s.own_cells(), s.state, s.red + 4 * kMaxPartials, s.red_counters + 5);
         return 48.0 * n;
     }
     if (name == "direction") {
-        LAUNCH(k_direction, g1, 256, 0, s.stream, s.d, (const double *)s.q, s.n, (const PcgState *)s.state, 0);
+        launch_direction(s, s.q, 0, false);
         return 24.0 * n;
     }
     return -1.0;
@@ -173,13 +191,14 @@ static void poll_state(Solver &s)
 int pcg_solve(Solver &s, const BoundaryValues &bv, double rel_tol, int max_iter, apm_lcl_scalars *sc)
 {
     const Fine5 v5 = s.view5();
-    const int g0 = grid_for(s, s.nz, s.nx, 8);
+    const int g0 = grid_for(s, s.zhi - s.zlo, s.nx, 8);
     const int g1 = s.num_sms * 8;
     double *part = s.red;                 // slots 0..15 belong to pcg.cu / conductance / flux
     unsigned int *cnt = s.red_counters;
-    const size_t n = s.n;
-    // cells per poll: small maps are launch bound, so look at the flag less often
+    const size_t n = s.n, own = s.own_cells();
+    // cells per poll: small maps are launch bound, so look at the flag less often (the same on every rank)
     const int check_every = (n >= (size_t)4 << 20 || getenv("APM_LCL_DEBUG")) ? 1 : (n >= (size_t)1 << 18 ? 2 : 4);
+    const bool striped = s.levels[0].striped;
 
     PcgState h{};
     h.tol2 = rel_tol * rel_tol;
@@ -188,7 +207,7 @@ int pcg_solve(Solver &s, const BoundaryValues &bv, double rel_tol, int max_iter,
         const double ps = fmax(fmax(fabs(bv.left), fabs(bv.right)), fmax(fabs(bv.bottom), fabs(bv.top)));
         const char *knob = getenv("APM_LCL_DX_TOL");   // relative; 2.5e-7 keeps weakly connected cells within the 1e-6 parity bar
         h.dx_tol = (knob ? atof(knob) : 2.5e-7) * (ps > 0 ? ps : 1.0);
-        h.dx = h.dx_prev = h.dx_prev2 = 1e300;
+        h.dx = h.dx_prev = h.dx_prev2 = h.dx_part = 1e300;
     }
     const bool debug = getenv("APM_LCL_DEBUG") != nullptr;
     CUDA_CHECK(cudaMemcpyAsync(s.state, &h, sizeof h, cudaMemcpyHostToDevice, s.stream));
@@ -196,7 +215,7 @@ int pcg_solve(Solver &s, const BoundaryValues &bv, double rel_tol, int max_iter,
     // z = M^-1 r lands in s.q: the cycle is out of place and q (= A d) is dead by then; the next
     // spmv overwrites it after the direction update has consumed it
     mg_vcycle(s, s.r, s.z, s.q, s.state, true);
-    LAUNCH(k_direction, g1, 256, 0, s.stream, s.d, (const double *)s.q, n, (const PcgState *)s.state, 1);
+    launch_direction(s, s.q, 1, false);
 
     int iters = 0, restarts = 0;
     bool done = false;
@@ -208,16 +227,16 @@ int pcg_solve(Solver &s, const BoundaryValues &bv, double rel_tol, int max_iter,
         return 0;
     }
     auto enqueue_iteration = [&]() {
-        LAUNCH_DEP(k_spmv5, g0, kBlock, 0, s.stream, v5, (const double *)s.d, s.q, s.state, part, cnt);
-        LAUNCH_DEP(k_update, g1, 256, 0, s.stream, s.x, s.r, (const double *)s.d, (const double *)s.q, n, s.state,
-               part + 4 * kMaxPartials, cnt + 5);
+        LAUNCH_DEP(k_spmv5, g0, kBlock, 0, s.stream, v5, (const double *)s.d, s.q, s.state, part, cnt, s.dist);
+        LAUNCH_DEP(k_update, g1, 256, 0, s.stream, s.own(s.x), s.own(s.r), (const double *)s.own(s.d),
+                   (const double *)s.own(s.q), own, s.state, part + 4 * kMaxPartials, cnt + 5);
         mg_vcycle(s, s.r, s.z, s.q, s.state, false);
-        LAUNCH_DEP(k_direction, g1, 256, 0, s.stream, s.d, (const double *)s.q, n, (const PcgState *)s.state, 0);
+        launch_direction(s, s.q, 0, true);
     };
 #ifndef LCL_CPU_SIM
     // Every argument of the steady-state iteration is a pointer or size fixed for the solver's lifetime
-    // (the scalars live in s.state on the device), so the ~45 launches are captured once into a CUDA
-    // graph and replayed: small maps are launch bound otherwise.
+    // (the scalars live in s.state on the device, the exchange counters in the slab), so the launches are
+    // captured once into a CUDA graph and replayed: small maps are launch bound otherwise.
     if (!s.iter_graph && !getenv("APM_LCL_NO_GRAPH")) {
         const long long before = g_launches;
         cudaGraph_t graph = nullptr;
@@ -240,23 +259,39 @@ int pcg_solve(Solver &s, const BoundaryValues &bv, double rel_tol, int max_iter,
 #endif
         enqueue_iteration();
     };
+    auto peer_error = [&]() {
+        if (s.world == 1) return false;
+        int e = 0;
+        CUDA_CHECK(cudaMemcpyAsync(&e, &s.dist.local->error, sizeof e, cudaMemcpyDeviceToHost, s.stream));
+        CUDA_CHECK(cudaStreamSynchronize(s.stream));
+        return e != 0;
+    };
     while (!done) {
         while (iters < max_iter) {
             for (int k = 0; k < check_every && iters < max_iter; k++, iters++) run_iteration();
             poll_state(s);
             if (debug)
-                fprintf(stderr, "[pcg] it %3d rr/bb %.3e rs/bs %.3e rz %.3e dq %.3e alpha %.3e beta %.3e dx %.3e conv %d fail %d\n",
-                        s.state_host->iter, sqrt(s.state_host->rr / bb), sqrt(s.state_host->rs / bs), s.state_host->rz,
+                fprintf(stderr, "[pcg %d/%d] it %3d rr/bb %.3e rs/bs %.3e rz %.3e dq %.3e alpha %.3e beta %.3e dx %.3e conv %d fail %d\n",
+                        s.rank, s.world, s.state_host->iter, sqrt(s.state_host->rr / bb), sqrt(s.state_host->rs / bs), s.state_host->rz,
                         s.state_host->dq, s.state_host->alpha, s.state_host->beta, s.state_host->dx,
                         s.state_host->converged, s.state_host->failed);
             if (s.state_host->converged || s.state_host->failed) break;
         }
         const int dev_iters = s.state_host->iter;
         // verify on the true residual (the recurrence can drift under 1e16 contrast)
+        if (striped) {
+            HaloSet hs;
+            hs.add(s.x);
+            halo_exchange(s, hs, s.nx, s.levels[0].cut, 1, 1, nullptr);
+        }
         LAUNCH(k_true_residual, g0, kBlock, 0, s.stream, v5, bv, (const double *)s.x, s.q, s.scal + 12,
-               part + 8 * kMaxPartials, cnt + 2);
+               part + 8 * kMaxPartials, cnt + 2, s.dist);
         CUDA_CHECK(cudaMemcpyAsync(s.scal_host + 12, s.scal + 12, 2 * sizeof(double), cudaMemcpyDeviceToHost, s.stream));
         CUDA_CHECK(cudaStreamSynchronize(s.stream));
+        if (peer_error()) {
+            g_last_error = "striped solve: a peer rank did not answer (wait timed out)";
+            return -1;
+        }
         true_rr = s.scal_host[12]; true_rs = s.scal_host[13];
         const bool ok = true_rr <= h.tol2 * bb && true_rs <= h.tol2 * bs;
         iters = dev_iters;
@@ -275,14 +310,14 @@ int pcg_solve(Solver &s, const BoundaryValues &bv, double rel_tol, int max_iter,
         } else {
             // restart from the true residual: r := b - A x, z = M^-1 r, d = z
             restarts++;
-            CUDA_CHECK(cudaMemcpyAsync(s.r, s.q, n * sizeof(double), cudaMemcpyDeviceToDevice, s.stream));
+            CUDA_CHECK(cudaMemcpyAsync(s.own(s.r), s.own(s.q), own * sizeof(double), cudaMemcpyDeviceToDevice, s.stream));
             PcgState h2 = *s.state_host;
             h2.converged = 0; h2.failed = 0;
             CUDA_CHECK(cudaMemcpyAsync(s.state, &h2, sizeof h2, cudaMemcpyHostToDevice, s.stream));
             CUDA_CHECK(cudaStreamSynchronize(s.stream));
             mg_vcycle(s, s.r, s.z, s.q, s.state, false);
             // after this cycle beta = rz_new/rz_old is meaningless: force a steepest-descent restart
-            LAUNCH(k_direction, g1, 256, 0, s.stream, s.d, (const double *)s.q, n, (const PcgState *)s.state, 1);
+            launch_direction(s, s.q, 1, false);
             poll_state(s);
             if (s.state_host->converged) {
                 // the cycle's own test passed on the true residual it was given

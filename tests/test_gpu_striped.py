@@ -1,0 +1,130 @@
+"""One map striped over several ranks on the GPU (-m gpu), through libapmlcl.so: ghost rows and dot products
+cross the cuts by peer stores and flags inside the kernels (csrc/dist.cuh, csrc/peer.cu).  The result must be
+the single-GPU result: the strips run the same iteration, only the order of the dot-product sums differs.
+
+Two ways to run the ranks: threads of this process (lcl.StripedGroup: peers addressed directly; with every
+rank on GPU 0 this also runs on a single-GPU box) and one process per rank over CUDA IPC (what torchrun /
+bench.py --gpus N do; needs >= 2 GPUs)."""
+import os
+import pickle
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from helpers import anchored_open_mask, synth_aperture
+from oracle import oracle_binding as ob
+from apmapflow_b200 import lcl
+from apmapflow_b200._lib import Params, LEFT, TOP, BOTTOM
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def synth_params(**kw):
+    base = dict(inlet_pressure=1000.0, outlet_pressure=0.0, density=1000.0, viscosity=1.0e-3,
+                voxel_size=10.0e-6, avg_factor=1.0, roughness=0.0, high_mask=100.0, low_mask=1e-4,
+                outlet_side=TOP)
+    base.update(kw)
+    return Params.defaults(**base)
+
+
+def gpu_count():
+    import torch
+    return torch.cuda.device_count()
+
+
+def compare_with_single(whole, s, f1, s1):
+    assert s["converged"] == 1
+    assert (s["zeros"], s["masked"], s["min_aper"], s["max_aper"]) == (s1["zeros"], s1["masked"], s1["min_aper"], s1["max_aper"])
+    assert abs(s["iterations"] - s1["iterations"]) <= 1
+    assert s["flow"] == pytest.approx(s1["flow"], rel=1e-9)
+    assert np.abs(whole["pressure"] - f1["pressure"]).max() <= 2e-7 * np.abs(f1["pressure"]).max()
+    assert np.array_equal(whole["aperture"], f1["aperture"])
+    for k in ("flow_x", "flow_z", "flow_m"):
+        assert np.abs(whole[k] - f1[k]).max() <= 1e-6 * np.abs(f1["flow_m"]).max()
+    assert np.nanmax(whole["residual"]) == 1.0
+
+
+@pytest.mark.parametrize("world,shape,side", [(2, (512, 384), TOP), (3, (700, 300), LEFT), (4, (1024, 256), BOTTOM)])
+def test_strips_on_one_gpu_match_the_single_solve_and_the_oracle_recipe(monkeypatch, world, shape, side):
+    """Every rank on GPU 0 (threads, shared device): the whole striped control flow on a single-GPU box."""
+    monkeypatch.setenv("APM_LCL_STRIPE_MIN_CELLS", "3000")
+    nz, nx = shape
+    a = synth_aperture(nz, nx, seed=nz + world, sigma_c=6, contact=0.15, sigma_k=10)
+    p = synth_params(outlet_side=side)
+    with lcl.StripedGroup(nx, nz, [0] * world) as g:
+        assert [r[:2] for r in g.rows][0][0] == 0 and g.rows[-1][1] == nz and len(g.rows) == world
+        assert all(g.rows[k][1] == g.rows[k + 1][0] for k in range(world - 1))      # the strips tile the map
+        whole, s = g.solve(p, a)
+        again, s_again = g.solve(p, a)
+        assert np.array_equal(whole["pressure"], again["pressure"])                 # deterministic, also across ranks
+        assert len({sc["flow"] for sc in s["per_rank"]}) == 1
+    f1, s1 = lcl.lcl_solve(p, a)
+    compare_with_single(whole, s, f1, s1)
+
+
+def test_strips_vs_oracle_small(monkeypatch):
+    monkeypatch.setenv("APM_LCL_STRIPE_MIN_CELLS", "1000")
+    a = synth_aperture(256, 200, seed=9, sigma_c=6, contact=0.15, sigma_k=10)
+    p = synth_params()
+    whole, s = lcl.lcl_solve_striped(p, a, [0, 0])
+    o, so = ob.solve(p, a)
+    mask = anchored_open_mask(a)
+    assert (s["zeros"], s["masked"]) == (so["zeros"], so["masked"])
+    assert (np.abs(whole["pressure"] - o["pressure"]) / 1000.0)[mask].max() < 1e-6
+    assert s["flow"] == pytest.approx(so["flow"], rel=1e-6)
+    assert np.array_equal(whole["aperture"], o["width"])
+
+
+def test_rate_bc_and_back_pressure_striped(monkeypatch):
+    monkeypatch.setenv("APM_LCL_STRIPE_MIN_CELLS", "3000")
+    a = synth_aperture(384, 256, seed=2, sigma_c=6)
+    p = synth_params(outlet_side=BOTTOM, inlet_pressure=-1.0, outlet_pressure=2.0e6, inlet_rate=1e-9)
+    whole, s = lcl.lcl_solve_striped(p, a, [0, 0, 0])
+    f1, s1 = lcl.lcl_solve(p, a)
+    assert s["outlet_rate"] == pytest.approx(1e-9, rel=1e-6)
+    assert s["inlet_pressure"] == pytest.approx(s1["inlet_pressure"], rel=1e-9)
+    assert np.abs(whole["flow_z"] - f1["flow_z"]).max() <= 1e-6 * np.abs(f1["flow_z"]).max()
+
+
+WORKER = r"""
+import os, sys, pickle
+sys.path[:0] = [{root!r}, os.path.join({root!r}, 'netl-ap-map-flow_b200'), os.path.join({root!r}, 'tests')]
+import numpy as np, torch, torch.distributed as dist
+from helpers import synth_aperture
+from apmapflow_b200 import lcl
+from apmapflow_b200._lib import Params
+rank, world = int(os.environ['RANK']), int(os.environ['WORLD_SIZE'])
+torch.cuda.set_device(rank)
+dist.init_process_group('gloo')
+nz, nx = {nz}, {nx}
+a = synth_aperture(nz, nx, seed=5, sigma_c=8, contact=0.2, sigma_k=16)
+p = Params.defaults(inlet_pressure=1000.0, outlet_pressure=0.0, density=1000.0, viscosity=1e-3, voxel_size=1e-5,
+                    avg_factor=1.0, high_mask=100.0, low_mask=1e-4, outlet_side='TOP')
+with lcl.StripedLclSolver(nx, nz, device=rank) as solver:
+    f, s = solver.solve(p, torch.from_numpy(a[solver.a_lo:solver.a_hi]).cuda(rank))
+    whole = solver.gather(f)
+if rank == 0:
+    f1, s1 = lcl.lcl_solve(p, a, device=0)
+    pickle.dump((whole, s, f1, s1), open({out!r}, 'wb'))
+dist.destroy_process_group()
+"""
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_one_process_per_gpu_over_cuda_ipc(tmp_path, world):
+    """torchrun-style: one process per GPU, slabs mapped through CUDA IPC, stores over NVLink."""
+    if gpu_count() < world:
+        pytest.skip("needs %d GPUs" % world)
+    nz, nx = 2048, 1536
+    script, out = tmp_path / "worker.py", tmp_path / "out.pkl"
+    script.write_text(WORKER.format(root=ROOT, nz=nz, nx=nx, out=str(out)))
+    port = 29500 + os.getpid() % 2000
+    env = dict(os.environ, APM_LCL_STRIPE_MIN_CELLS="20000")
+    subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world),
+                    "--master-addr", "127.0.0.1", "--master-port", str(port), str(script)], check=True, env=env,
+                   timeout=600)
+    whole, s, f1, s1 = pickle.load(open(out, "rb"))
+    compare_with_single(whole, s, f1, s1)

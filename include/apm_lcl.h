@@ -133,6 +133,11 @@ APM_LCL_API int apm_lcl_solver_connect(apm_lcl_solver *s, const void *handles);
 APM_LCL_API int apm_lcl_solver_disconnect(apm_lcl_solver *s);
 APM_LCL_API int apm_lcl_solver_rows(apm_lcl_solver *s, int *z_lo, int *z_hi, int *a_lo, int *a_hi);
 
+/* The same from ONE process: `n_devices` strips, one solver and one host thread per entry of `devices` (a GPU
+ * may be named more than once), the strips' memory addressed directly.  Whole-map HOST buffers in and out. */
+APM_LCL_API int apm_lcl_solve_striped(const apm_lcl_params *p, const double *aperture, int nx, int nz, int n_devices,
+                                      const int *devices, apm_lcl_fields *out, apm_lcl_scalars *sc);
+
 /* One-shot convenience (create + solve + destroy) on `device`. */
 APM_LCL_API int apm_lcl_solve(const apm_lcl_params *p, const double *aperture, int nx, int nz, int device,
                   apm_lcl_fields *out, apm_lcl_scalars *sc);
@@ -147,13 +152,18 @@ APM_LCL_API int apm_lcl_solve(const apm_lcl_params *p, const double *aperture, i
 APM_LCL_API int apm_lcl_bulk_solve(int device, int nx, int nz, int n_cases, const apm_lcl_params *params,
                                    const double *const *apertures, apm_lcl_fields *outs, apm_lcl_scalars *scalars);
 
-/* File-level entry point: what `apm-lcl-model.exe file.inp` does (APERTURE_MAP_FLOW.F:1-51).  Reads the
+/* File-level entry point: what `apm-lcl-model.exe file.inp` does (APERTURE_MAP_FLOW.F:1-51).  With the
+ * environment variable APM_LCL_DEVICES="0,1,2,3" the map is striped over those GPUs (apm_lcl_solve_striped) and
+ * `device` is ignored.  Reads the
  * initialization file (OPEN_IO IO_MODULE.F:51, READ_MASTER APERTURE_MAP_FLOW.F:191), the aperture map
  * (READ_DATA_MAP MAP_MODULE.F:18), runs the hot path on `device` and writes the log, stat (csv+yaml),
  * aperture, flow-x/z/m, pressure and VTK files in the reference's formats.  The transcript the
  * reference prints to stdout is returned in `log` (NUL terminated, truncated at the front if longer
  * than log_cap).  Returns 0, or 1 with the reference's error messages in the transcript. */
 APM_LCL_API int apm_lcl_run_file(const char *inp_path, int device, char *log, size_t log_cap);
+/* The same with the map striped over `devices` (what run_model(..., devices=[...]) calls). */
+APM_LCL_API int apm_lcl_run_file_striped(const char *inp_path, const int *devices, int n_devices, char *log,
+                                         size_t log_cap);
 
 /* Kernel-level entry points used by the parity tests -------------------------------------- */
 

@@ -77,7 +77,8 @@ EXPORTS = (
     "apm_lcl_conductance", "apm_lcl_solver_device_field", "apm_lcl_solver_time_kernel",
     "apm_lcl_run_file", "apm_lcl_bulk_solve",
     "apm_lcl_peer_handle_bytes", "apm_lcl_solver_create_striped", "apm_lcl_solver_connect",
-    "apm_lcl_solver_disconnect", "apm_lcl_solver_rows",
+    "apm_lcl_solver_disconnect", "apm_lcl_solver_rows", "apm_lcl_solve_striped",
+    "apm_lcl_run_file_striped",
 )
 
 _lib = None
@@ -112,6 +113,8 @@ def bind(lib):
     lib.apm_lcl_solver_connect.argtypes = [C.c_void_p, C.c_void_p]
     lib.apm_lcl_solver_disconnect.argtypes = [C.c_void_p]
     lib.apm_lcl_solver_rows.argtypes = [C.c_void_p] + [C.POINTER(C.c_int)] * 4
+    lib.apm_lcl_solve_striped.argtypes = [C.POINTER(Params), C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int),
+                                          C.POINTER(Fields), C.POINTER(Scalars)]
     lib.apm_lcl_solver_solve.argtypes = [C.c_void_p, C.POINTER(Params), C.c_void_p,
                                          C.POINTER(Fields), C.POINTER(Scalars)]
     lib.apm_lcl_solve.argtypes = [C.POINTER(Params), C.c_void_p, C.c_int, C.c_int, C.c_int,
@@ -127,6 +130,8 @@ def bind(lib):
     lib.apm_lcl_bulk_solve.restype = C.c_int
     lib.apm_lcl_run_file.argtypes = [C.c_char_p, C.c_int, C.c_char_p, C.c_size_t]
     lib.apm_lcl_run_file.restype = C.c_int
+    lib.apm_lcl_run_file_striped.argtypes = [C.c_char_p, C.POINTER(C.c_int), C.c_int, C.c_char_p, C.c_size_t]
+    lib.apm_lcl_run_file_striped.restype = C.c_int
     return lib
 
 

@@ -245,7 +245,8 @@ def estimate_req_RAM(input_maps, avail_RAM=float("inf"), suppress=False, **kwarg
 class LclProcess(object):
     """Popen-compatible handle of an in-process model run (what ``run_model`` returns)."""
 
-    def __init__(self, input_file, device, show_stdout):
+    def __init__(self, input_file, device, show_stdout, devices=None):
+        self.devices = [int(d) for d in devices] if devices else None
         self.input_file = input_file
         self.args = ("libapmlcl.so:apm_lcl_run_file", input_file.outfile_name)
         self.pid = os.getpid()
@@ -267,7 +268,12 @@ class LclProcess(object):
         try:
             lib = _lib.load()
             buf = C.create_string_buffer(_LOG_CAP)
-            rc = lib.apm_lcl_run_file(os.fsencode(self.input_file.outfile_name), int(self.device), buf, _LOG_CAP)
+            name = os.fsencode(self.input_file.outfile_name)
+            if self.devices and len(self.devices) > 1:      # one map cut into row strips over these GPUs
+                devs = (C.c_int * len(self.devices))(*self.devices)
+                rc = lib.apm_lcl_run_file_striped(name, devs, len(self.devices), buf, _LOG_CAP)
+            else:
+                rc = lib.apm_lcl_run_file(name, int(self.device), buf, _LOG_CAP)
             out, err = buf.value.decode("utf-8", "replace"), ""
         except Exception as exc:   # missing library etc.: fail loudly through the handle
             rc, out, err = 1, "", "{}: {}".format(type(exc).__name__, exc)
@@ -324,12 +330,13 @@ def _lcl_library_setup():
     return lib
 
 
-def run_model(input_file_obj, synchronous=False, show_stdout=False, device=0):
+def run_model(input_file_obj, synchronous=False, show_stdout=False, device=0, devices=None):
     """Runs one LCL simulation described by an ``InputFile`` (reference :710-772).
 
     The input file is (re)written to ``input_file_obj.outfile_name`` first, exactly like the
     reference.  Returns a Popen-like handle; with ``synchronous=True`` it has finished on return.
-    ``device`` (new) selects the GPU."""
+    ``device`` (new) selects the GPU; ``devices`` (new) names several GPUs of this node to cut one large map
+    into row strips over (one solver per GPU inside this process)."""
     input_file_obj.write_inp_file()
     default_exe = os.path.join(DEFAULT_MODEL_PATH, DEFAULT_MODEL_NAME)
     exe = os.path.abspath(input_file_obj.executable or default_exe)
@@ -338,6 +345,8 @@ def run_model(input_file_obj, synchronous=False, show_stdout=False, device=0):
         logger.debug("Using executable located at: " + exe)
         out = None if show_stdout else PIPE
         env = dict(os.environ, APM_LCL_DEVICE=str(device))
+        if devices:
+            env["APM_LCL_DEVICES"] = ",".join(str(int(d)) for d in devices)
         proc = Popen((exe, input_file_obj.outfile_name), stdout=out, stderr=out, universal_newlines=True, env=env)
         proc.input_file = input_file_obj
         proc.start_time = time.time()
@@ -348,7 +357,7 @@ def run_model(input_file_obj, synchronous=False, show_stdout=False, device=0):
             comm.join()
         return proc
     _lcl_library_setup()          # raises OSError when libapmlcl.so is missing: no CPU fallback
-    proc = LclProcess(input_file_obj, device, show_stdout)
+    proc = LclProcess(input_file_obj, devices[0] if devices else device, show_stdout, devices=devices)
     logger.info("Beginning Simulation:\n\tInput File: {} \n\tProcess ID: {}".format(input_file_obj.outfile_name, proc.pid))
     if synchronous:
         proc.wait()

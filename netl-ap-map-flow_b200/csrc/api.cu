@@ -482,6 +482,73 @@ int apm_lcl_solve(const apm_lcl_params *p, const double *aperture, int nx, int n
     return rc;
 }
 
+int apm_lcl_solve_striped(const apm_lcl_params *p, const double *aperture, int nx, int nz, int n_devices,
+                          const int *devices, apm_lcl_fields *out, apm_lcl_scalars *sc)
+{
+    // One process, one solver and one host thread per strip; the strips' slabs are addressed directly
+    // (same process), so this needs no rendezvous at all.  Host buffers only: a whole-map device buffer
+    // would live on ONE of the GPUs.
+    if (n_devices <= 1) return apm_lcl_solve(p, aperture, nx, nz, (devices && n_devices == 1) ? devices[0] : 0, out, sc);
+    std::vector<apm_lcl_solver *> h((size_t)n_devices, nullptr);
+    auto cleanup = [&]() {
+        for (auto *x : h)
+            if (x) apm_lcl_solver_disconnect(x);
+        for (auto *x : h)
+            if (x) apm_lcl_solver_destroy(x);
+    };
+    API_TRY
+    if (!p || !aperture || !devices) throw CudaError{"params / aperture / devices pointer is NULL"};
+    if (n_devices > kMaxRanks) throw CudaError{"too many strips"};
+    if (is_device_ptr(aperture)) throw CudaError{"apm_lcl_solve_striped takes host buffers"};
+    std::vector<char> blobs((size_t)n_devices * kPeerHandleBytes);
+    for (int k = 0; k < n_devices; k++)
+        if (apm_lcl_solver_create_striped(&h[k], devices[k], nx, nz, k, n_devices, blobs.data() + (size_t)k * kPeerHandleBytes))
+            throw CudaError{g_last_error};
+    for (int k = 0; k < n_devices; k++)
+        if (apm_lcl_solver_connect(h[k], blobs.data())) throw CudaError{g_last_error};
+    std::vector<apm_lcl_scalars> scal((size_t)n_devices);
+    std::vector<std::string> errors((size_t)n_devices);
+    std::vector<int> rcs((size_t)n_devices, 0);
+    std::vector<long long> launches((size_t)n_devices, 0);
+    std::vector<std::thread> pool;
+    for (int k = 0; k < n_devices; k++)
+        pool.emplace_back([&, k]() {
+            const Solver &s = *h[k]->s;
+            const size_t in_off = (size_t)ap_lo(s) * nx, out_off = (size_t)s.zlo * nx;
+            apm_lcl_fields fo{};
+            if (out) {
+                double *const src[7] = {out->pressure, out->flow_x, out->flow_z, out->flow_m, out->aperture, out->reynolds, out->residual};
+                double **dst[7] = {&fo.pressure, &fo.flow_x, &fo.flow_z, &fo.flow_m, &fo.aperture, &fo.reynolds, &fo.residual};
+                for (int f = 0; f < 7; f++) *dst[f] = src[f] ? src[f] + out_off : nullptr;
+            }
+            rcs[k] = apm_lcl_solver_solve(h[k], p, aperture + in_off, &fo, &scal[k]);
+            errors[k] = g_last_error;
+            launches[k] = g_launches;
+        });
+    for (auto &t : pool) t.join();
+    long long total = 0;
+    for (int k = 0; k < n_devices; k++) total += launches[k];
+    if (sc) *sc = scal[0];
+    for (int k = 0; k < n_devices; k++)
+        if (rcs[k]) throw CudaError{errors[k]};
+    cleanup();
+    g_launches = total;
+    g_last_error.clear();
+    return 0;
+    }
+    catch (const CudaError &e) {
+        const std::string msg = e.msg;
+        cleanup();
+        g_last_error = msg;
+        return 1;
+    }
+    catch (...) {
+        cleanup();
+        g_last_error = "unknown error";
+        return 1;
+    }
+}
+
 int apm_lcl_bulk_solve(int device, int nx, int nz, int n_cases, const apm_lcl_params *params,
                        const double *const *apertures, apm_lcl_fields *outs, apm_lcl_scalars *scalars)
 {

@@ -889,7 +889,7 @@ int side_code(const std::string &s)
     return -1;
 }
 
-int run(Run &r, int device)
+int run(Run &r, const std::vector<int> &devices)
 {
     // defaults, APERTURE_MAP_FLOW.F:88-126
     apm_lcl_default_params(&r.p);
@@ -952,7 +952,10 @@ int run(Run &r, int device)
         // the file pipeline prints 8-12 significant digits and is dominated by ASCII I/O: converge two
         // orders tighter than the tensor API's 1e-10 default so the printed digits are the solution's
         if (!(r.p.rel_tol > 0)) r.p.rel_tol = 1e-12;
-        solve_rc = apm_lcl_solve(&r.p, r.ap.data(), nx, nz, device, &fo, &sc);
+        // several devices: the map is cut into row strips over those GPUs
+        if (devices.size() > 1)
+            solve_rc = apm_lcl_solve_striped(&r.p, r.ap.data(), nx, nz, (int)devices.size(), devices.data(), &fo, &sc);
+        else solve_rc = apm_lcl_solve(&r.p, r.ap.data(), nx, nz, devices.empty() ? 0 : devices[0], &fo, &sc);
         if (solve_rc) solve_err = apm_lcl_last_error();
         timer.lap("apm_lcl_solve (host buffers)");
     }
@@ -1235,7 +1238,7 @@ int run(Run &r, int device)
 
 }   // namespace
 
-extern "C" APM_LCL_API int apm_lcl_run_file(const char *inp_path, int device, char *log, size_t log_cap)
+static int run_file(const char *inp_path, const std::vector<int> &devices, char *log, size_t log_cap)
 {
     Run r;
     int rc = 1;
@@ -1244,7 +1247,7 @@ extern "C" APM_LCL_API int apm_lcl_run_file(const char *inp_path, int device, ch
     } else {
         r.inp = inp_path;
         try {
-            rc = run(r, device);
+            rc = run(r, devices);
         } catch (const std::exception &e) {
             r.to_stdout(std::string(" ERROR - ") + e.what());
             rc = 1;
@@ -1261,4 +1264,26 @@ extern "C" APM_LCL_API int apm_lcl_run_file(const char *inp_path, int device, ch
         log[m] = '\0';
     }
     return rc;
+}
+
+extern "C" APM_LCL_API int apm_lcl_run_file(const char *inp_path, int device, char *log, size_t log_cap)
+{
+    // APM_LCL_DEVICES="0,1,2,3" (the executable's way to name several GPUs) overrides `device`
+    std::vector<int> devices;
+    if (const char *e = getenv("APM_LCL_DEVICES")) {
+        std::stringstream ss(e);
+        std::string tok;
+        while (std::getline(ss, tok, ','))
+            if (!tok.empty()) devices.push_back(atoi(tok.c_str()));
+    }
+    if (devices.empty()) devices.push_back(device);
+    return run_file(inp_path, devices, log, log_cap);
+}
+
+extern "C" APM_LCL_API int apm_lcl_run_file_striped(const char *inp_path, const int *devices, int n_devices, char *log,
+                                                    size_t log_cap)
+{
+    std::vector<int> devs(devices, devices + (devices && n_devices > 0 ? n_devices : 0));
+    if (devs.empty()) devs.push_back(0);
+    return run_file(inp_path, devs, log, log_cap);
 }

@@ -128,3 +128,50 @@ def test_one_process_per_gpu_over_cuda_ipc(tmp_path, world):
                    timeout=600)
     whole, s, f1, s1 = pickle.load(open(out, "rb"))
     compare_with_single(whole, s, f1, s1)
+
+
+def test_c_level_one_shot_striped_solve(monkeypatch):
+    """apm_lcl_solve_striped: whole-map host buffers in and out, strips driven by the library's own threads."""
+    import ctypes as C
+    from apmapflow_b200 import _lib
+    from apmapflow_b200._lib import Fields, Scalars
+    monkeypatch.setenv("APM_LCL_STRIPE_MIN_CELLS", "3000")
+    lib = _lib.load()
+    nz, nx = 320, 272
+    a = synth_aperture(nz, nx, seed=21, sigma_c=6, contact=0.1, sigma_k=10)
+    p = synth_params()
+    pres, qz = np.empty((nz, nx)), np.empty((nz, nx))
+    fo, sc = Fields(pressure=pres.ctypes.data, flow_z=qz.ctypes.data), Scalars()
+    devs = (C.c_int * 3)(0, 0, 0)
+    assert lib.apm_lcl_solve_striped(C.byref(p), a.ctypes.data, nx, nz, 3, devs, C.byref(fo), C.byref(sc)) == 0, _lib.last_error()
+    f1, s1 = lcl.lcl_solve(p, a, fields=("pressure", "flow_z"))
+    assert sc.converged == 1 and sc.flow == pytest.approx(s1["flow"], rel=1e-9)
+    assert np.abs(pres - f1["pressure"]).max() <= 2e-7 * 1000.0
+    assert np.abs(qz - f1["flow_z"]).max() <= 1e-6 * np.abs(f1["flow_z"]).max()
+    assert lib.apm_lcl_last_launch_count() > 0
+
+
+def test_run_model_with_devices_writes_the_same_files(tmp_path, monkeypatch):
+    """The file-level drop-in with the map striped over several 'devices': run_model(devices=[...]) must write
+    what the single-GPU run writes (the formatted digits are the same solution)."""
+    from apmapflow_b200.run_model import InputFile, run_model
+    monkeypatch.setenv("APM_LCL_STRIPE_MIN_CELLS", "2000")
+    golden = os.path.join(ROOT, "tests", "golden")
+    outs = {}
+    for tag, devices in (("one", None), ("striped", [0, 0])):
+        work = tmp_path / tag
+        work.mkdir()
+        inp = InputFile(os.path.join(golden, "test-model-inputs.txt"))
+        for key in ("APER-MAP", "SUMMARY-FILE", "STAT-FILE", "APER-FILE", "FLOW-FILE", "PRESS-FILE", "VTK-FILE"):
+            inp[key].commented_out = False
+        for key in ("SUMMARY-FILE", "STAT-FILE", "APER-FILE", "FLOW-FILE", "PRESS-FILE", "VTK-FILE"):
+            inp.filename_formats[key] = os.path.join(str(work), key + ".out")
+        inp.filename_formats["input_file"] = os.path.join(str(work), "case.inp")
+        inp["APER-MAP"] = os.path.join(golden, "Fracture1ApertureMap-10avg.txt")
+        proc = run_model(inp, synchronous=True, devices=devices)
+        assert proc.poll() == 0, proc.stdout_content
+        outs[tag] = work
+    for name in ("PRESS-FILE.out", "FLOW-FILE-z.out", "FLOW-FILE-x.out", "APER-FILE.out"):
+        a = np.loadtxt(outs["one"] / name, delimiter=",")
+        b = np.loadtxt(outs["striped"] / name, delimiter=",")
+        assert np.abs(a - b).max() <= 1e-6 * np.abs(a).max(), name

@@ -72,6 +72,8 @@ static void layout(Solver &s, Arena &a)
     mg_allocate(s, a);
 }
 
+__global__ void k_side_inflow(Fine5 v, const double *__restrict__ p, int side, double pb, double *out, Dist dc);
+
 static Solver *solver_new(int device, int nx, int nz, int rank, int world, void *handle_out)
 {
     int count = 0;
@@ -93,6 +95,8 @@ static Solver *solver_new(int device, int nx, int nz, int rank, int world, void 
         s->num_sms = prop.multiProcessorCount;
         CUDA_CHECK(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
         CUDA_CHECK(cudaStreamCreateWithFlags(&s->copy_stream, cudaStreamNonBlocking));
+        preload_conductance(); preload_flux(); preload_pcg(); preload_peer(); preload_cycle(); preload_setup();
+        preload_one(k_side_inflow);
         mg_plan(*s);
         Arena count_pass;
         layout(*s, count_pass);

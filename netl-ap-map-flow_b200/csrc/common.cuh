@@ -76,6 +76,28 @@ inline void cuda_check(cudaError_t e, const char *what, const char *file, int li
 #define LAUNCH_DEP LAUNCH
 #endif
 
+// Loads a kernel into the current device's context.  CUDA loads kernels lazily, at their first launch, and
+// that load synchronises with the context: a rank spinning on a peer's flag would then keep the peer --
+// another solver of the same process on the same GPU -- from ever launching the kernel that raises the flag.
+// Every solver therefore loads all kernels when it is created (also keeps first-launch cost out of timings).
+#ifndef LCL_CPU_SIM
+template <class K>
+inline void preload_one(K kernel)
+{
+    cudaFuncAttributes attr;
+    CUDA_CHECK(cudaFuncGetAttributes(&attr, kernel));
+}
+#else
+template <class K>
+inline void preload_one(K) {}
+#endif
+void preload_conductance();
+void preload_flux();
+void preload_pcg();
+void preload_peer();
+void preload_cycle();
+void preload_setup();
+
 inline int div_up(long long a, long long b) { return (int)((a + b - 1) / b); }
 
 // ---------------------------------------------------------------------------------------------
@@ -176,7 +198,10 @@ struct PeerWindow {
 struct DistLocal {                                // local bookkeeping of the same sequence (never written by peers)
     unsigned long long halo_seq, gather_seq, bcast_seq;
     unsigned int block_counter[4];                // "last block done" of the exchange kernels
-    int error;                                    // a wait timed out
+    int error;                                    // a wait timed out: 1 halo, 2 gather, 3 broadcast (first one wins)
+    int error_peer;                               // ... on the flag of this rank
+    unsigned long long error_want, error_have;    // ... which should have reached / had reached this count
+    unsigned long long timeout_ns;                // how long a wait may last (APM_LCL_PEER_TIMEOUT_MS, default 20 s)
 };
 struct Dist {
     int rank = 0, world = 1;
@@ -288,6 +313,7 @@ constexpr int kPeerHandleBytes = 128;
 void slab_create(Solver &s, size_t bytes, void *handle_out);   // one zeroed allocation (+ its IPC handle if world > 1)
 void slab_connect(Solver &s, const void *handles);             // maps the peers' slabs, fills s.dist
 void slab_disconnect(Solver &s);
+std::string peer_error_report(Solver &s);   // "" unless a wait on a peer timed out
 void slab_destroy(Solver &s);
 struct HaloSet {
     double *a[12];

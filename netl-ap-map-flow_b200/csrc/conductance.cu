@@ -235,4 +235,11 @@ void export_reference_layout(Solver &s, double *trx_dev, double *trz_dev)
     LAUNCH(k_export_layout, s.num_sms * 4, 256, 0, s.stream, s.view5(), trx_dev, trz_dev);
 }
 
+// forces the kernels of this file into the device's context now (see preload_kernels, api.cu)
+void preload_conductance()
+{
+    preload_one(k_conductance);
+    preload_one(k_export_layout);
+}
+
 }   // namespace lcl

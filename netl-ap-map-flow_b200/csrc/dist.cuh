@@ -72,11 +72,11 @@ __device__ __forceinline__ unsigned long long now_ns()
 __device__ __forceinline__ void spin_pause() { __nanosleep(64); }
 #endif
 
-constexpr unsigned long long kWaitTimeoutNs = 20ull * 1000 * 1000 * 1000;   // a peer that is 20 s late is gone
-
-// Wait until the local flag *p has reached `want`.  Bounded: on time-out the rank records the error and
-// carries on with whatever it has, every later wait returns at once, and the host reports the failure.
-__device__ __forceinline__ bool wait_flag(const unsigned long long *p, unsigned long long want, const Dist &dc)
+// Wait until the local flag *p (raised by rank `peer`) has reached `want`.  Bounded (DistLocal::timeout_ns, 20 s
+// unless APM_LCL_PEER_TIMEOUT_MS says otherwise): on time-out the rank records which wait it was and carries on
+// with whatever it has, every later wait returns at once, and the host reports the failure.
+__device__ __forceinline__ bool wait_flag(const unsigned long long *p, unsigned long long want, const Dist &dc, int kind,
+                                          int peer)
 {
     if (ld_acquire_sys(p) >= want) return true;
     if (dc.local->error) return false;
@@ -86,8 +86,11 @@ __device__ __forceinline__ bool wait_flag(const unsigned long long *p, unsigned 
             if (ld_acquire_sys(p) >= want) return true;
             spin_pause();
         }
-        if (now_ns() - t0 > kWaitTimeoutNs) {
-            dc.local->error = 1;
+        if (now_ns() - t0 > dc.local->timeout_ns) {
+            dc.local->error = kind;
+            dc.local->error_peer = peer;
+            dc.local->error_want = want;
+            dc.local->error_have = ld_acquire_sys(p);
             return false;
         }
     }
@@ -116,7 +119,7 @@ __device__ LCL_NOINLINE void dist_gather(const Dist &dc, const double (&mine)[NV
     fence_sys();
     for (int r = 0; r < dc.world; r++) st_release_sys(&dc.win[r]->gather_flag[dc.rank], seq);
     PeerWindow *self = dc.win[dc.rank];
-    for (int r = 0; r < dc.world; r++) wait_flag(&self->gather_flag[r], seq, dc);
+    for (int r = 0; r < dc.world; r++) wait_flag(&self->gather_flag[r], seq, dc, 2, r);
     fence_sys();
     for (int r = 0; r < dc.world; r++)
 #pragma unroll

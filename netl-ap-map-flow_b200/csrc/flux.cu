@@ -135,4 +135,12 @@ void launch_affine(Solver &s, double *x, size_t n, double scale, double shift)
     LAUNCH(k_affine, s.num_sms * 8, 256, 0, s.stream, x, n, scale, shift);
 }
 
+// forces the kernels of this file into the device's context now (see preload_kernels, api.cu)
+void preload_flux()
+{
+    preload_one(k_flux);
+    preload_one(k_normalise);
+    preload_one(k_affine);
+}
+
 }   // namespace lcl

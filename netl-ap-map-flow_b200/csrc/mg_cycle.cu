@@ -1118,4 +1118,20 @@ void mg_vcycle(Solver &s, const double *r, double *ztmp, double *zout, PcgState 
     }
 }
 
+// forces the kernels of this file into the device's context now (see preload_kernels, api.cu)
+void preload_cycle()
+{
+    preload_one(k_residual9);
+    preload_one((k_smooth9<true, false, true>));
+    preload_one((k_smooth9<false, false, true>));
+    preload_one((k_smooth9<false, true, false>));
+    preload_one(k_down5);
+    preload_one(k_up5);
+    preload_one(k_restrict);
+    preload_one(k_tail_cycle);
+    preload_one(k_coarse_solve);
+    preload_one(k_copy);
+    preload_one(k_dot_norms);
+}
+
 }   // namespace lcl

@@ -449,4 +449,18 @@ void mg_setup(Solver &s)
     LAUNCH(k_coarse_inverse, 1, 256, smem, s.stream, last.view9(), s.coarse_inv, s.coarse_scale, n);
 }
 
+// forces the kernels of this file into the device's context now (see preload_kernels, api.cu)
+void preload_setup()
+{
+    preload_one((k_weights_edges<F5>));
+    preload_one((k_weights_edges<C9>));
+    preload_one((k_weights_centres<F5>));
+    preload_one((k_weights_centres<C9>));
+    preload_one((k_galerkin<F5>));
+    preload_one((k_galerkin<C9>));
+    preload_one(k_coarse_diag);
+    preload_one(k_coarse_inverse);
+    preload_one(k_fine_as_coarse);
+}
+
 }   // namespace lcl

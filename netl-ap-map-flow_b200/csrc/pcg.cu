@@ -220,7 +220,18 @@ int pcg_solve(Solver &s, const BoundaryValues &bv, double rel_tol, int max_iter,
     int iters = 0, restarts = 0;
     bool done = false;
     double true_rr = 0.0, true_rs = 0.0, bb = 0.0, bs = 0.0;
+    auto peer_error = [&]() {
+        if (s.world == 1) return false;
+        int e = 0;
+        CUDA_CHECK(cudaMemcpyAsync(&e, &s.dist.local->error, sizeof e, cudaMemcpyDeviceToHost, s.stream));
+        CUDA_CHECK(cudaStreamSynchronize(s.stream));
+        return e != 0;
+    };
     poll_state(s);
+    if (peer_error()) {   // a peer went missing during the set-up or the first cycle
+        g_last_error = peer_error_report(s);
+        return -1;
+    }
     bb = s.state_host->bb; bs = s.state_host->bs;
     if (!(bb > 0.0)) {   // zero right-hand side: x = 0 is the solution
         if (sc) { sc->iterations += 0; sc->converged = 1; sc->rel_residual = 0.0; sc->rel_residual_scaled = 0.0; }
@@ -259,13 +270,6 @@ int pcg_solve(Solver &s, const BoundaryValues &bv, double rel_tol, int max_iter,
 #endif
         enqueue_iteration();
     };
-    auto peer_error = [&]() {
-        if (s.world == 1) return false;
-        int e = 0;
-        CUDA_CHECK(cudaMemcpyAsync(&e, &s.dist.local->error, sizeof e, cudaMemcpyDeviceToHost, s.stream));
-        CUDA_CHECK(cudaStreamSynchronize(s.stream));
-        return e != 0;
-    };
     while (!done) {
         while (iters < max_iter) {
             for (int k = 0; k < check_every && iters < max_iter; k++, iters++) run_iteration();
@@ -289,7 +293,7 @@ int pcg_solve(Solver &s, const BoundaryValues &bv, double rel_tol, int max_iter,
         CUDA_CHECK(cudaMemcpyAsync(s.scal_host + 12, s.scal + 12, 2 * sizeof(double), cudaMemcpyDeviceToHost, s.stream));
         CUDA_CHECK(cudaStreamSynchronize(s.stream));
         if (peer_error()) {
-            g_last_error = "striped solve: a peer rank did not answer (wait timed out)";
+            g_last_error = peer_error_report(s);
             return -1;
         }
         true_rr = s.scal_host[12]; true_rs = s.scal_host[13];
@@ -326,6 +330,16 @@ int pcg_solve(Solver &s, const BoundaryValues &bv, double rel_tol, int max_iter,
         }
     }
     return iters;
+}
+
+// forces the kernels of this file into the device's context now (see preload_kernels, api.cu)
+void preload_pcg()
+{
+    preload_one(k_init_rhs);
+    preload_one(k_spmv5);
+    preload_one(k_update);
+    preload_one(k_direction);
+    preload_one(k_true_residual);
 }
 
 }   // namespace lcl

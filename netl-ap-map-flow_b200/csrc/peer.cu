@@ -6,6 +6,7 @@
 // north star names NCCL send/recv for the 1-cell halo; a PCG + multigrid iteration has ~30 such points, each
 // a few hundred KB at most, so what matters is latency: a peer store plus a flag costs a few microseconds
 // inside the stream, an NCCL call an order of magnitude more, and both ride the same NVLink.
+#include <cstdlib>
 #include <cstring>
 #include <string>
 
@@ -146,7 +147,35 @@ void slab_connect(Solver &s, const void *handles)
         s.dist.win[r] = (PeerWindow *)s.peer_slab[r];
         s.dist.peer_off[r] = (long long)((char *)s.peer_slab[r] - s.slab);
     }
+    unsigned long long timeout_ns = 20ull * 1000 * 1000 * 1000;   // a peer that is 20 s late is gone
+    if (const char *e = getenv("APM_LCL_PEER_TIMEOUT_MS")) timeout_ns = (unsigned long long)atoll(e) * 1000 * 1000;
+    CUDA_CHECK(cudaMemcpyAsync(&s.dist.local->timeout_ns, &timeout_ns, sizeof timeout_ns, cudaMemcpyHostToDevice, s.stream));
+    CUDA_CHECK(cudaStreamSynchronize(s.stream));
     s.connected = true;
+}
+
+// what the host says when a wait timed out: which wait, on whom, and where both sides' counters stand
+std::string peer_error_report(Solver &s)
+{
+    if (s.world == 1) return "";
+    DistLocal loc{};
+    PeerWindow win{};
+    cudaMemcpy(&loc, s.dist.local, sizeof loc, cudaMemcpyDeviceToHost);
+    cudaMemcpy(&win, s.dist.win[s.rank], sizeof win, cudaMemcpyDeviceToHost);
+    if (!loc.error) return "";
+    static const char *kinds[] = {"?", "halo exchange", "gather of partial sums", "row broadcast"};
+    char buf[512];
+    snprintf(buf, sizeof buf,
+             "striped solve: rank %d of %d gave up waiting in a %s for rank %d (flag at %llu, expected %llu); own counts: "
+             "halo %llu gather %llu broadcast %llu; flags seen: halo below %llu above %llu",
+             s.rank, s.world, kinds[loc.error >= 1 && loc.error <= 3 ? loc.error : 0], loc.error_peer, loc.error_have,
+             loc.error_want, loc.halo_seq, loc.gather_seq, loc.bcast_seq, win.halo_flag[0], win.halo_flag[1]);
+    std::string msg = buf;
+    msg += "; gather flags";
+    for (int r = 0; r < s.world; r++) msg += " " + std::to_string(win.gather_flag[r]);
+    msg += "; broadcast flags";
+    for (int r = 0; r < s.world; r++) msg += " " + std::to_string(win.bcast_flag[r]);
+    return msg;
 }
 
 void slab_disconnect(Solver &s)
@@ -212,8 +241,8 @@ k_halo_exchange(Dist dc, HaloSet hs, int pitch, int zlo, int zhi, int zlo_dn, in
         if (dn) st_release_sys(&dc.win[dc.rank - 1]->halo_flag[1], seq);   // I am the rank above my lower neighbour
         if (up) st_release_sys(&dc.win[dc.rank + 1]->halo_flag[0], seq);
         PeerWindow *self = dc.win[dc.rank];
-        if (dn) wait_flag(&self->halo_flag[0], seq, dc);
-        if (up) wait_flag(&self->halo_flag[1], seq, dc);
+        if (dn) wait_flag(&self->halo_flag[0], seq, dc, 1, dc.rank - 1);
+        if (up) wait_flag(&self->halo_flag[1], seq, dc, 1, dc.rank + 1);
         fence_sys();
     }
 }
@@ -235,7 +264,7 @@ k_row_broadcast(Dist dc, HaloSet hs, int pitch, int z0, int z1, const PcgState *
                 if (r != dc.rank) st_release_sys(&dc.win[r]->bcast_flag[dc.rank], seq + 1);
         }
         for (int r = 0; r < dc.world; r++)
-            if (r != dc.rank) wait_flag(&self->bcast_flag[r], seq + 1, dc);
+            if (r != dc.rank) wait_flag(&self->bcast_flag[r], seq + 1, dc, 3, r);
         fence_sys();
     }
     __syncthreads();
@@ -247,7 +276,7 @@ k_row_broadcast(Dist dc, HaloSet hs, int pitch, int z0, int z1, const PcgState *
         for (int r = 0; r < dc.world; r++)
             if (r != dc.rank) st_release_sys(&dc.win[r]->bcast_flag[dc.rank], seq + 2);
         for (int r = 0; r < dc.world; r++)
-            if (r != dc.rank) wait_flag(&self->bcast_flag[r], seq + 2, dc);
+            if (r != dc.rank) wait_flag(&self->bcast_flag[r], seq + 2, dc, 3, r);
         fence_sys();
     }
 }
@@ -276,6 +305,13 @@ void row_broadcast(Solver &s, const HaloSet &hs, int pitch, const int *cut, cons
     const int z0 = cut[s.rank], z1 = cut[s.rank + 1];
     const long long elements = (long long)(z1 - z0) * pitch * hs.count * (s.world - 1);
     LAUNCH_DEP(k_row_broadcast, xchg_grid(s, elements), 256, 0, s.stream, s.dist, hs, pitch, z0, z1, st);
+}
+
+// forces the kernels of this file into the device's context now (see preload_kernels, api.cu)
+void preload_peer()
+{
+    preload_one(k_halo_exchange);
+    preload_one(k_row_broadcast);
 }
 
 }   // namespace lcl

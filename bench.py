@@ -269,7 +269,10 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: there is no CPU fallback")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa_cores = 0
     if world > 1:
+        from apmapflow_b200 import dist as apm_dist
+        numa_cores = apm_dist.bind_to_gpu_numa(local)     # pinned buffers land on the GPU's own NUMA node
         dist.init_process_group("nccl", device_id=dev)
 
     def barrier():
@@ -423,6 +426,7 @@ def main():
                                    "contact cells (sigma=16), constant-pressure inlet/outlet (1000 -> 0 Pa, TOP), %s"
                                    % (n, n, 100 * args.contact, how),
                        "cells_per_gpu": own_cells, "rel_tol": 1e-10, "pcg_iterations": iters / args.steps,
+                       "host_cores_bound_to_gpu_numa_node": numa_cores,
                        "l2": "inputs larger than L2 (%.0f MB per field vs 126 MB)" % (8 * cells / 1e6),
                        "host_wall_ms_per_step": wall_ms / args.steps,
                        "setup_ms": last["setup_ms"], "solve_ms": last["solve_ms"],

@@ -8,7 +8,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(os.path.dirname(_HERE), "libapmlcl.so")
+# APM_LCL_LIB: developer knob for A/B runs of two builds of the SAME library (never a different implementation)
+LIB_PATH = os.environ.get("APM_LCL_LIB") or os.path.join(os.path.dirname(_HERE), "libapmlcl.so")
 
 LEFT, RIGHT, TOP, BOTTOM = 0, 1, 2, 3
 SIDE_NAMES = ("LEFT", "RIGHT", "TOP", "BOTTOM")

@@ -403,7 +403,7 @@ def main():
     if rank != 0:
         return finish()
     traffic = None
-    tpath = os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")
+    tpath = os.path.join(ROOT, "profiles", "r02_ncu_traffic.json")     # ncu capture of these kernels (tools/r02_measure.sh)
     if os.path.exists(tpath) and world == 1:
         tj = json.load(open(tpath))
         if tj.get("size") == n and dom in tj["kernels"]:

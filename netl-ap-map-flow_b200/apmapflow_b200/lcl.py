@@ -30,11 +30,15 @@ class LclSolver(object):
             raise _lib.LclError((self.lib.apm_lcl_last_error() or b"").decode())
 
     def close(self):
-        if self._h:
+        if getattr(self, "_h", None):
             self.lib.apm_lcl_solver_destroy(self._h)
-            self._h = C.c_void_p()
+            self._h = None
 
-    __del__ = close
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:      # interpreter shutdown: the modules this needs may already be gone
+            pass
 
     def __enter__(self):
         return self

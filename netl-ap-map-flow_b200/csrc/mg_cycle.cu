@@ -373,6 +373,22 @@ static_assert(kDnW == 64 && kDnH % kDnWarps == 0, "a framed row is two lane roun
 static_assert(kDnTX / 2 <= 32, "a row of coarse points per warp");
 static_assert(2 * (kDnSmem + 2048) <= 228 * 1024, "two blocks per SM");
 
+// 1 / d for the diagonals of the smoothers (d > 0, far from the ends of the exponent range): hardware seed
+// (upper 32 bits, ~2^-23) and two Newton steps, 5 instructions without the range checks and the slow path of
+// an IEEE division.  The last bit may differ from 1.0 / d; both legs of the cycle use this same function of the
+// same sum, so the preconditioner stays symmetric.
+__device__ __forceinline__ double rcp_diag(double d)
+{
+#ifdef LCL_CPU_SIM
+    return 1.0 / d;
+#else
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));
+    r = fma(fma(-d, r, 1.0), r, r);
+    return fma(fma(-d, r, 1.0), r, r);
+#endif
+}
+
 // Shared-memory layout of a framed row: the 32 even columns first, then the 32 odd ones, so the lanes
 // of a warp walking one colour (stride 2 in x) touch consecutive doubles -- no bank conflicts -- and so
 // do their left/right neighbours (the other parity) and the rows above and below.
@@ -382,10 +398,27 @@ __device__ __forceinline__ int dn_pos(int row, int col) { return row * kDnW + (c
 // of a framed H x 64 tile whose frame is F cells on the low sides, asynchronously and zero-filled
 // outside the grid.  Lanes 0-15 take the even columns of a 32-column chunk, lanes 16-31 the odd ones:
 // one contiguous 256-byte read, two conflict-free 128-byte shared-memory writes.
-template <int F, int H>
+// INT (interior tile: the whole framed region lies inside the rows this rank holds and inside the grid): no
+// predicates, no zero fill, one address per row.
+template <int F, int H, bool INT>
 __device__ __forceinline__ void stage_tile5(double *sb, double *stx, double *stz, const Fine5 &v,
                                             const double *__restrict__ b, int z0, int x0, int wy, int lane)
 {
+    if (INT) {
+        const int col0 = 2 * (lane & 15) + (lane >> 4);
+        size_t i = (size_t)(z0 + wy - F) * v.nx + (x0 - F + col0);
+        int k = dn_pos(wy, col0);                      // dn_pos(row, col0 + 32) = k + 16
+#pragma unroll
+        for (int row = wy; row < H; row += kDnWarps, i += (size_t)kDnWarps * v.nx, k += kDnWarps * kDnW) {
+            cp_async8(&sb[k], b + i, true);
+            cp_async8(&stx[k], v.tx + i, true);
+            cp_async8(&stz[k], v.tz + i, true);
+            cp_async8(&sb[k + 16], b + i + 32, true);
+            cp_async8(&stx[k + 16], v.tx + i + 32, true);
+            cp_async8(&stz[k + 16], v.tz + i + 32, true);
+        }
+        return;
+    }
     // rows this rank holds (strip + ghost rows; the whole grid on one GPU).  Row -1 of the grid is the bottom
     // boundary face tzb; the row below a strip's ghost rows is not held and reads as 0 (it only feeds ghost
     // cells nobody uses)
@@ -410,132 +443,147 @@ __device__ __forceinline__ void stage_tile5(double *sb, double *stx, double *stz
     }
 }
 
+// One tile of the down leg.  INT: interior tile (every cell of the framed region exists and is held, the whole
+// tile is owned, nx even): the passes run without a single bounds test -- 97 % of the tiles of a large map.
+template <bool INT>
+__device__ __forceinline__ void down5_tile(double *smem, const Fine5 &v, const Weights &w, const double *__restrict__ b,
+                                           double *__restrict__ x, double *__restrict__ bc, int nzc, int nxc, int czhi, int z0,
+                                           int x0, int rlo, int rhi, double (&acc)[2])
+{
+    constexpr int W = kDnW, H = kDnH, FL = kDnFL, TZ = kDnTZ, TX = kDnTX;
+    double *sb = smem, *stx = smem + H * W, *stz = smem + 2 * H * W, *sx = smem + 3 * H * W;
+    const int nz = v.nz, nx = v.nx, zhi = v.zhi;
+    const int lane = threadIdx.x & 31, wy = threadIdx.x >> 5;
+    stage_tile5<FL, H, INT>(sb, stx, stz, v, b, z0, x0, wy, lane);
+    // restriction weights of this thread's coarse points (rows wy, wy + 16 of the tile's 21 x 29) ride along
+    constexpr int CR = (TZ / 2 + kDnWarps - 1) / kDnWarps;
+    const int X = x0 / 2 + lane;
+    double wne[CR], wnw[CR], wse[CR], wsw[CR];
+    bool cin[CR];
+#pragma unroll
+    for (int c = 0; c < CR; c++) {
+        const int cr = wy + c * kDnWarps, Z = z0 / 2 + cr;
+        cin[c] = cr < TZ / 2 && lane < TX / 2 && (INT || (Z < czhi && X < nxc));
+        wne[c] = wnw[c] = wse[c] = wsw[c] = 0.0;
+        if (cin[c]) {
+            const size_t bk = (size_t)Z * nxc + X;
+            const bool xm = INT || X > 0, xp = INT || 2 * X + 1 < nx, zm = INT || Z > 0, zp = INT || 2 * Z + 1 < nz;
+            if (zp && xp) wne[c] = w.csw[bk];
+            if (zp && xm) wnw[c] = w.cse[bk - 1];
+            if (zm && xp) wse[c] = w.cnw[bk - nxc];
+            if (zm && xm) wsw[c] = w.cne[bk - nxc - 1];
+        }
+    }
+    cp_async_wait_all();
+    __syncthreads();
+    // ---- red cells ((lz + lx) even; z0, x0 are even), rows -3..TZ+1, columns -3..TX+1
+#pragma unroll
+    for (int row = wy; row < TZ + 5; row += kDnWarps) {
+        const int lz = row - 3, lx = 2 * lane - 3 + ((lz & 1) ^ 1);
+        if (lx > TX + 1) continue;
+        const int z = z0 + lz, xx = x0 + lx, par = (lx + FL) & 1;
+        const int p = dn_pos(lz + FL, lx + FL), pl = p + (par ? -32 : 31);
+        double val = 0.0;
+        if (INT || (z >= rlo && z < rhi && xx >= 0 && xx < nx)) {
+            const double bi = sb[p];
+            const double inv = rcp_diag((stx[pl] + stx[p]) + (stz[p - W] + stz[p]));
+            val = bi * inv;
+            if (lz >= 0 && lz < TZ && (INT || z < zhi) && lx >= 0 && lx < TX) { acc[0] += bi * bi; acc[1] += bi * bi * inv; }
+        }
+        sx[p] = val;
+    }
+    __syncthreads();
+    // ---- black cells, rows -2..TZ, columns -2..TX (neighbours outside the grid hold 0)
+#pragma unroll
+    for (int row = wy; row < TZ + 3; row += kDnWarps) {
+        const int lz = row - 2, lx = 2 * lane - 2 + ((lz & 1) ^ 1);
+        if (lx > TX) continue;
+        const int z = z0 + lz, xx = x0 + lx, par = (lx + FL) & 1;
+        const int p = dn_pos(lz + FL, lx + FL), pl = p + (par ? -32 : 31), pr = p + (par ? -31 : 32);
+        double val = 0.0;
+        if (INT || (z >= rlo && z < rhi && xx >= 0 && xx < nx)) {
+            const double tl = stx[pl], tr = stx[p], td = stz[p - W], tu = stz[p];
+            const double bi = sb[p];
+            double s = bi;
+            s += tl * sx[pl];
+            s += tr * sx[pr];
+            s += td * sx[p - W];
+            s += tu * sx[p + W];
+            const double inv = rcp_diag((tl + tr) + (td + tu));
+            val = s * inv;
+            if (lz >= 0 && lz < TZ && (INT || z < zhi) && lx >= 0 && lx < TX) { acc[0] += bi * bi; acc[1] += bi * bi * inv; }
+        }
+        sx[p] = val;
+    }
+    __syncthreads();
+    // ---- residual at red cells, rows -1..TZ-1, columns -1..TX-1, in place over b (it is 0 at black cells)
+#pragma unroll
+    for (int row = wy; row < TZ + 1; row += kDnWarps) {
+        const int lz = row - 1, lx = 2 * lane - 1 + ((lz & 1) ^ 1);
+        if (lx > TX - 1) continue;
+        const int z = z0 + lz, xx = x0 + lx, par = (lx + FL) & 1;
+        const int p = dn_pos(lz + FL, lx + FL), pl = p + (par ? -32 : 31), pr = p + (par ? -31 : 32);
+        if (INT || (z >= rlo && z < rhi && xx >= 0 && xx < nx)) {
+            const double xi = sx[p];
+            double s = sb[p];
+            s -= stx[pl] * (xi - sx[pl]);
+            s -= stx[p] * (xi - sx[pr]);
+            s -= stz[p - W] * (xi - sx[p - W]);
+            s -= stz[p] * (xi - sx[p + W]);
+            sb[p] = s;
+        }
+    }
+    // ---- x of the tile, out of place (independent of the residual pass: no barrier needed before it)
+#pragma unroll
+    for (int lz = wy; lz < TZ; lz += kDnWarps) {
+        const int z = z0 + lz, xe = x0 + 2 * lane;
+        if (lane >= TX / 2 || (!INT && (z >= zhi || xe >= nx))) continue;
+        const size_t i = (size_t)z * nx + xe;
+        const int p = dn_pos(lz + FL, 2 * lane + FL);      // even column; its right neighbour is at p + 32
+        const double v0 = sx[p], v1 = sx[p + 32];
+        if (INT || (xe + 1 < nx && !(nx & 1))) {
+            *reinterpret_cast<double2 *>(x + i) = make_double2(v0, v1);   // i even when nx even: aligned
+        } else {
+            x[i] = v0;
+            if (xe + 1 < nx) x[i + 1] = v1;
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int c = 0; c < CR; c++)
+        if (cin[c]) {
+            const int cr = wy + c * kDnWarps;
+            const int p = dn_pos(2 * cr + FL, 2 * lane + FL);  // even column: left neighbour p + 31, right p + 32
+            double s = sb[p];
+            s += wne[c] * sb[p + W + 32];
+            s += wnw[c] * sb[p + W + 31];
+            s += wse[c] * sb[p - W + 32];
+            s += wsw[c] * sb[p - W + 31];
+            bc[(size_t)(z0 / 2 + cr) * nxc + X] = s;
+        }
+    __syncthreads();
+}
+
 __global__ void __launch_bounds__(kDnThreads, 2)
 k_down5(Fine5 v, Weights w, const double *__restrict__ b, double *__restrict__ x, double *__restrict__ bc, int nzc,
         int nxc, int czhi, PcgState *st, int init, double *partials, unsigned int *counter, Dist dc)
 {
     if (stopped(st)) return;
-    constexpr int W = kDnW, H = kDnH, FL = kDnFL, TZ = kDnTZ, TX = kDnTX;
+    constexpr int FL = kDnFL, FH = kDnFH, TZ = kDnTZ, TX = kDnTX;
     LCL_DYNAMIC_SMEM(double, smem);
-    double *sb = smem, *stx = smem + H * W, *stz = smem + 2 * H * W, *sx = smem + 3 * H * W;
     // a strip tiles its own rows [zlo, zhi) (zlo even) and owns the coarse rows below czhi; cells exist for it
     // in the rows [rlo, rhi) it holds.  The frame of a tile at a cut is recomputed from the ghost rows of b and
     // of the faces exactly as inside the grid: the sweep is exact red/black, so the result does not depend on
     // where tiles or strips are cut.
     const int nz = v.nz, nx = v.nx, zlo = v.zlo, zhi = v.zhi, rlo = read_lo(zlo), rhi = read_hi(zhi, nz);
     const int tiles_x = (nx + TX - 1) / TX, tiles_z = (zhi - zlo + TZ - 1) / TZ;
-    const int lane = threadIdx.x & 31, wy = threadIdx.x >> 5;
     double acc[2] = {0.0, 0.0};
     for (long long t = blockIdx.x; t < (long long)tiles_x * tiles_z; t += gridDim.x) {
         const int z0 = zlo + (int)(t / tiles_x) * TZ, x0 = (int)(t % tiles_x) * TX;
-        stage_tile5<FL, H>(sb, stx, stz, v, b, z0, x0, wy, lane);
-        // restriction weights of this thread's coarse points (rows wy, wy + 16 of the tile's 21 x 29) ride along
-        constexpr int CR = (TZ / 2 + kDnWarps - 1) / kDnWarps;
-        const int X = x0 / 2 + lane;
-        double wne[CR], wnw[CR], wse[CR], wsw[CR];
-        bool cin[CR];
-#pragma unroll
-        for (int c = 0; c < CR; c++) {
-            const int cr = wy + c * kDnWarps, Z = z0 / 2 + cr;
-            cin[c] = cr < TZ / 2 && lane < TX / 2 && Z < czhi && X < nxc;
-            wne[c] = wnw[c] = wse[c] = wsw[c] = 0.0;
-            if (cin[c]) {
-                const size_t bk = (size_t)Z * nxc + X;
-                const bool xm = X > 0, xp = 2 * X + 1 < nx, zm = Z > 0, zp = 2 * Z + 1 < nz;
-                if (zp && xp) wne[c] = w.csw[bk];
-                if (zp && xm) wnw[c] = w.cse[bk - 1];
-                if (zm && xp) wse[c] = w.cnw[bk - nxc];
-                if (zm && xm) wsw[c] = w.cne[bk - nxc - 1];
-            }
-        }
-        cp_async_wait_all();
-        __syncthreads();
-        // ---- red cells ((lz + lx) even; z0, x0 are even), rows -3..TZ+1, columns -3..TX+1
-#pragma unroll
-        for (int row = wy; row < TZ + 5; row += kDnWarps) {
-            const int lz = row - 3, lx = 2 * lane - 3 + ((lz & 1) ^ 1);
-            if (lx > TX + 1) continue;
-            const int z = z0 + lz, xx = x0 + lx, par = (lx + FL) & 1;
-            const int p = dn_pos(lz + FL, lx + FL), pl = p + (par ? -32 : 31);
-            double val = 0.0;
-            if (z >= rlo && z < rhi && xx >= 0 && xx < nx) {
-                const double bi = sb[p];
-                const double inv = 1.0 / ((stx[pl] + stx[p]) + (stz[p - W] + stz[p]));
-                val = bi * inv;
-                if (lz >= 0 && lz < TZ && z < zhi && lx >= 0 && lx < TX) { acc[0] += bi * bi; acc[1] += bi * bi * inv; }
-            }
-            sx[p] = val;
-        }
-        __syncthreads();
-        // ---- black cells, rows -2..TZ, columns -2..TX (neighbours outside the grid hold 0)
-#pragma unroll
-        for (int row = wy; row < TZ + 3; row += kDnWarps) {
-            const int lz = row - 2, lx = 2 * lane - 2 + ((lz & 1) ^ 1);
-            if (lx > TX) continue;
-            const int z = z0 + lz, xx = x0 + lx, par = (lx + FL) & 1;
-            const int p = dn_pos(lz + FL, lx + FL), pl = p + (par ? -32 : 31), pr = p + (par ? -31 : 32);
-            double val = 0.0;
-            if (z >= rlo && z < rhi && xx >= 0 && xx < nx) {
-                const double tl = stx[pl], tr = stx[p], td = stz[p - W], tu = stz[p];
-                const double bi = sb[p];
-                double s = bi;
-                s += tl * sx[pl];
-                s += tr * sx[pr];
-                s += td * sx[p - W];
-                s += tu * sx[p + W];
-                const double inv = 1.0 / ((tl + tr) + (td + tu));
-                val = s * inv;
-                if (lz >= 0 && lz < TZ && z < zhi && lx >= 0 && lx < TX) { acc[0] += bi * bi; acc[1] += bi * bi * inv; }
-            }
-            sx[p] = val;
-        }
-        __syncthreads();
-        // ---- residual at red cells, rows -1..TZ-1, columns -1..TX-1, in place over b (it is 0 at black cells)
-#pragma unroll
-        for (int row = wy; row < TZ + 1; row += kDnWarps) {
-            const int lz = row - 1, lx = 2 * lane - 1 + ((lz & 1) ^ 1);
-            if (lx > TX - 1) continue;
-            const int z = z0 + lz, xx = x0 + lx, par = (lx + FL) & 1;
-            const int p = dn_pos(lz + FL, lx + FL), pl = p + (par ? -32 : 31), pr = p + (par ? -31 : 32);
-            if (z >= rlo && z < rhi && xx >= 0 && xx < nx) {
-                const double xi = sx[p];
-                double s = sb[p];
-                s -= stx[pl] * (xi - sx[pl]);
-                s -= stx[p] * (xi - sx[pr]);
-                s -= stz[p - W] * (xi - sx[p - W]);
-                s -= stz[p] * (xi - sx[p + W]);
-                sb[p] = s;
-            }
-        }
-        // ---- x of the tile, out of place (independent of the residual pass: no barrier needed before it)
-#pragma unroll
-        for (int lz = wy; lz < TZ; lz += kDnWarps) {
-            const int z = z0 + lz, xe = x0 + 2 * lane;
-            if (lane >= TX / 2 || z >= zhi || xe >= nx) continue;
-            const size_t i = (size_t)z * nx + xe;
-            const int p = dn_pos(lz + FL, 2 * lane + FL);      // even column; its right neighbour is at p + 32
-            const double v0 = sx[p], v1 = sx[p + 32];
-            if (xe + 1 < nx && !(nx & 1)) {
-                *reinterpret_cast<double2 *>(x + i) = make_double2(v0, v1);   // i even when nx even: aligned
-            } else {
-                x[i] = v0;
-                if (xe + 1 < nx) x[i + 1] = v1;
-            }
-        }
-        __syncthreads();
-#pragma unroll
-        for (int c = 0; c < CR; c++)
-            if (cin[c]) {
-                const int cr = wy + c * kDnWarps;
-                const int p = dn_pos(2 * cr + FL, 2 * lane + FL);  // even column: left neighbour p + 31, right p + 32
-                double s = sb[p];
-                s += wne[c] * sb[p + W + 32];
-                s += wnw[c] * sb[p + W + 31];
-                s += wse[c] * sb[p - W + 32];
-                s += wsw[c] * sb[p - W + 31];
-                bc[(size_t)(z0 / 2 + cr) * nxc + X] = s;
-            }
-        __syncthreads();
+        const bool interior = !(nx & 1) && z0 - FL >= rlo && z0 + TZ + FH <= rhi && z0 + TZ <= zhi && x0 - FL >= 0 &&
+                              x0 + TX + FH <= nx;
+        if (interior) down5_tile<true>(smem, v, w, b, x, bc, nzc, nxc, czhi, z0, x0, rlo, rhi, acc);
+        else down5_tile<false>(smem, v, w, b, x, bc, nzc, nxc, czhi, z0, x0, rlo, rhi, acc);
     }
     grid_sum_finalize<2>(acc, partials, counter, [=](const double(&tot)[2]) { down_norms_finalize(st, init, tot, dc); });
 }
@@ -549,102 +597,120 @@ constexpr int kUpH = kUpTZ + 2 * kUpF;
 constexpr size_t kUpSmem = 4 * (size_t)kUpH * kDnW * sizeof(double);
 static_assert(kUpH == 2 * kDnWarps && kUpTX + 2 * kUpF == kDnW, "one coarse block per thread; rows as wide as the down leg's");
 
+// One tile of the up leg; INT as in down5_tile (plus: every coarse block of the framed tile, its upper and right
+// neighbours included, is held).
+template <bool INT>
+__device__ __forceinline__ void up5_tile(double *smem, const Fine5 &v, const double *__restrict__ b, const double *__restrict__ xin,
+                                         double *__restrict__ xout, const Weights &w, const double *__restrict__ e, int nzc,
+                                         int nxc, int blo, int bhi, int z0, int x0, int rlo, int rhi, double (&acc)[2])
+{
+    constexpr int W = kDnW, H = kUpH, F = kUpF, TZ = kUpTZ, TX = kUpTX;
+    double *sb = smem, *stx = smem + H * W, *stz = smem + 2 * H * W, *sx = smem + 3 * H * W;
+    const int nz = v.nz, nx = v.nx, zhi = v.zhi;
+    const int lane = threadIdx.x & 31, wy = threadIdx.x >> 5;
+    stage_tile5<F, H, INT>(sb, stx, stz, v, b, z0, x0, wy, lane);
+#pragma unroll
+    for (int br = wy; br < H / 2; br += kDnWarps) {
+        // x + P e of the coarse block (br, lane) of the framed tile: rows 2br, 2br+1, columns 2lane, 2lane+1
+        const int bz = (z0 >> 1) - 1 + br, bx = (x0 >> 1) - 1 + lane;
+        double v00 = 0.0, v01 = 0.0, v10 = 0.0, v11 = 0.0;
+        if (INT || (bz >= blo && bx >= 0 && bz < bhi && bx < nxc)) {
+            const size_t bk = (size_t)bz * nxc + bx;
+            const size_t i = (size_t)(2 * bz) * nx + 2 * bx;
+            const bool Xp = INT || bx + 1 < nxc, Zp = INT || bz + 1 < nzc;
+            const bool xp = INT || 2 * bx + 1 < nx, zp = INT || 2 * bz + 1 < nz;
+            const double e00 = e[bk];
+            const double e01 = Xp ? e[bk + 1] : 0.0;
+            const double e10 = Zp ? e[bk + nxc] : 0.0;
+            const double e11 = (Zp && Xp) ? e[bk + nxc + 1] : 0.0;
+            v00 = xin[i] + e00;
+            if (xp) v01 = xin[i + 1] + (w.hw[bk] * e00 + w.he[bk] * e01);
+            if (zp) v10 = xin[i + nx] + (w.vs[bk] * e00 + w.vn[bk] * e10);
+            if (zp && xp)
+                v11 = xin[i + nx + 1] + ((w.csw[bk] * e00 + w.cse[bk] * e01) + (w.cnw[bk] * e10 + w.cne[bk] * e11));
+        }
+        const int p = 2 * br * W + lane;               // dn_pos(2 br, 2 lane); the odd column sits 32 further
+        sx[p] = v00;
+        sx[p + 32] = v01;
+        sx[p + W] = v10;
+        sx[p + W + 32] = v11;
+    }
+    cp_async_wait_all();
+    __syncthreads();
+    // ---- black cells ((lz + lx) odd) of the tile and its first frame ring, rows -1..TZ, columns -1..TX
+#pragma unroll
+    for (int row = wy; row < TZ + 2; row += kDnWarps) {
+        const int lz = row - 1, lx = 2 * lane - 1 + (lz & 1);
+        if (lx > TX) continue;
+        const int z = z0 + lz, xx = x0 + lx, par = (lx + F) & 1;
+        const int p = dn_pos(lz + F, lx + F), pl = p + (par ? -32 : 31), pr = p + (par ? -31 : 32);
+        if (INT || (z >= rlo && z < rhi && xx >= 0 && xx < nx)) {
+            const double tl = stx[pl], tr = stx[p], td = stz[p - W], tu = stz[p];
+            double s = sb[p];
+            s += tl * sx[pl];
+            s += tr * sx[pr];
+            s += td * sx[p - W];
+            s += tu * sx[p + W];
+            sx[p] = s * rcp_diag((tl + tr) + (td + tu));
+        }
+    }
+    __syncthreads();
+    // ---- red cells of the tile: each lane owns a horizontal pair (one red cell to update, one black cell
+    // to copy), accumulates b.x over both and writes them out of place
+#pragma unroll
+    for (int lz = wy; lz < TZ; lz += kDnWarps) {
+        const int z = z0 + lz, xe = x0 + 2 * lane;
+        if (lane >= TX / 2 || (!INT && (z >= zhi || xe >= nx))) continue;
+        const size_t i = (size_t)z * nx + xe;
+        const int pe = dn_pos(lz + F, 2 * lane + F), po = pe + 32;
+        const int r = lz & 1;                          // 0: the even cell is red, 1: the odd cell is red
+        double v0 = sx[pe], v1 = sx[po];
+        if (INT || xe + r < nx) {
+            const int p = r ? po : pe, pl = r ? pe : pe + 31, pr = r ? po - 31 : po;
+            const double tl = stx[pl], tr = stx[p], td = stz[p - W], tu = stz[p];
+            double s = sb[p];
+            s += tl * sx[pl];
+            s += tr * sx[pr];
+            s += td * sx[p - W];
+            s += tu * sx[p + W];
+            const double xn = s * rcp_diag((tl + tr) + (td + tu));
+            if (r) v1 = xn; else v0 = xn;
+        }
+        acc[0] += sb[pe] * v0;
+        acc[0] += sb[po] * v1;                         // b and x are both 0 beyond the grid
+        if (INT || (xe + 1 < nx && !(nx & 1))) {
+            *reinterpret_cast<double2 *>(xout + i) = make_double2(v0, v1);   // i even when nx even: aligned
+        } else {
+            xout[i] = v0;
+            if (xe + 1 < nx) xout[i + 1] = v1;
+        }
+    }
+    __syncthreads();
+}
+
 __global__ void __launch_bounds__(kDnThreads, 2)
 k_up5(Fine5 v, const double *__restrict__ b, const double *__restrict__ xin, double *__restrict__ xout, Weights w,
       const double *__restrict__ e, int nzc, int nxc, int wlo, int whi, PcgState *st, int init, double *partials,
       unsigned int *counter, Dist dc)
 {
     if (stopped(st)) return;
-    constexpr int W = kDnW, H = kUpH, F = kUpF, TZ = kUpTZ, TX = kUpTX;
+    constexpr int F = kUpF, TZ = kUpTZ, TX = kUpTX, H = kUpH;
     LCL_DYNAMIC_SMEM(double, smem);
-    double *sb = smem, *stx = smem + H * W, *stz = smem + 2 * H * W, *sx = smem + 3 * H * W;
     // strip: own rows [zlo, zhi), held rows [rlo, rhi); coarse blocks whose weights, coarse values and fine
     // rows this rank holds: [blo, bhi)
     const int nz = v.nz, nx = v.nx, zlo = v.zlo, zhi = v.zhi, rlo = read_lo(zlo), rhi = read_hi(zhi, nz);
     const int blo = wlo > ((rlo + 1) >> 1) ? wlo : ((rlo + 1) >> 1), bhi = whi < ((rhi + 1) >> 1) ? whi : ((rhi + 1) >> 1);
     const int tiles_x = (nx + TX - 1) / TX, tiles_z = (zhi - zlo + TZ - 1) / TZ;
-    const int lane = threadIdx.x & 31, wy = threadIdx.x >> 5;
     double acc[2] = {0.0, 0.0};
     for (long long t = blockIdx.x; t < (long long)tiles_x * tiles_z; t += gridDim.x) {
         const int z0 = zlo + (int)(t / tiles_x) * TZ, x0 = (int)(t % tiles_x) * TX;
-        stage_tile5<F, H>(sb, stx, stz, v, b, z0, x0, wy, lane);
-#pragma unroll
-        for (int br = wy; br < H / 2; br += kDnWarps) {
-            // x + P e of the coarse block (br, lane) of the framed tile: rows 2br, 2br+1, columns 2lane, 2lane+1
-            const int bz = (z0 >> 1) - 1 + br, bx = (x0 >> 1) - 1 + lane;
-            double v00 = 0.0, v01 = 0.0, v10 = 0.0, v11 = 0.0;
-            if (bz >= blo && bx >= 0 && bz < bhi && bx < nxc) {
-                const size_t bk = (size_t)bz * nxc + bx;
-                const size_t i = (size_t)(2 * bz) * nx + 2 * bx;
-                const bool Xp = bx + 1 < nxc, Zp = bz + 1 < nzc;
-                const bool xp = 2 * bx + 1 < nx, zp = 2 * bz + 1 < nz;
-                const double e00 = e[bk];
-                const double e01 = Xp ? e[bk + 1] : 0.0;
-                const double e10 = Zp ? e[bk + nxc] : 0.0;
-                const double e11 = (Zp && Xp) ? e[bk + nxc + 1] : 0.0;
-                v00 = xin[i] + e00;
-                if (xp) v01 = xin[i + 1] + (w.hw[bk] * e00 + w.he[bk] * e01);
-                if (zp) v10 = xin[i + nx] + (w.vs[bk] * e00 + w.vn[bk] * e10);
-                if (zp && xp)
-                    v11 = xin[i + nx + 1] + ((w.csw[bk] * e00 + w.cse[bk] * e01) + (w.cnw[bk] * e10 + w.cne[bk] * e11));
-            }
-            const int p = 2 * br * W + lane;               // dn_pos(2 br, 2 lane); the odd column sits 32 further
-            sx[p] = v00;
-            sx[p + 32] = v01;
-            sx[p + W] = v10;
-            sx[p + W + 32] = v11;
-        }
-        cp_async_wait_all();
-        __syncthreads();
-        // ---- black cells ((lz + lx) odd) of the tile and its first frame ring, rows -1..TZ, columns -1..TX
-#pragma unroll
-        for (int row = wy; row < TZ + 2; row += kDnWarps) {
-            const int lz = row - 1, lx = 2 * lane - 1 + (lz & 1);
-            if (lx > TX) continue;
-            const int z = z0 + lz, xx = x0 + lx, par = (lx + F) & 1;
-            const int p = dn_pos(lz + F, lx + F), pl = p + (par ? -32 : 31), pr = p + (par ? -31 : 32);
-            if (z >= rlo && z < rhi && xx >= 0 && xx < nx) {
-                const double tl = stx[pl], tr = stx[p], td = stz[p - W], tu = stz[p];
-                double s = sb[p];
-                s += tl * sx[pl];
-                s += tr * sx[pr];
-                s += td * sx[p - W];
-                s += tu * sx[p + W];
-                sx[p] = s / ((tl + tr) + (td + tu));
-            }
-        }
-        __syncthreads();
-        // ---- red cells of the tile: each lane owns a horizontal pair (one red cell to update, one black cell
-        // to copy), accumulates b.x over both and writes them out of place
-#pragma unroll
-        for (int lz = wy; lz < TZ; lz += kDnWarps) {
-            const int z = z0 + lz, xe = x0 + 2 * lane;
-            if (lane >= TX / 2 || z >= zhi || xe >= nx) continue;
-            const size_t i = (size_t)z * nx + xe;
-            const int pe = dn_pos(lz + F, 2 * lane + F), po = pe + 32;
-            const int r = lz & 1;                          // 0: the even cell is red, 1: the odd cell is red
-            double v0 = sx[pe], v1 = sx[po];
-            if (xe + r < nx) {
-                const int p = r ? po : pe, pl = r ? pe : pe + 31, pr = r ? po - 31 : po;
-                const double tl = stx[pl], tr = stx[p], td = stz[p - W], tu = stz[p];
-                double s = sb[p];
-                s += tl * sx[pl];
-                s += tr * sx[pr];
-                s += td * sx[p - W];
-                s += tu * sx[p + W];
-                const double xn = s / ((tl + tr) + (td + tu));
-                if (r) v1 = xn; else v0 = xn;
-            }
-            acc[0] += sb[pe] * v0;
-            acc[0] += sb[po] * v1;                         // b and x are both 0 beyond the grid
-            if (xe + 1 < nx && !(nx & 1)) {
-                *reinterpret_cast<double2 *>(xout + i) = make_double2(v0, v1);   // i even when nx even: aligned
-            } else {
-                xout[i] = v0;
-                if (xe + 1 < nx) xout[i + 1] = v1;
-            }
-        }
-        __syncthreads();
+        // first and last coarse block row / column the framed tile touches (their upper / right neighbours included)
+        const int bz0 = (z0 >> 1) - 1, bz1 = bz0 + H / 2 - 1, bx0 = (x0 >> 1) - 1, bx1 = bx0 + 31;
+        const bool interior = !(nx & 1) && z0 - F >= rlo && z0 + TZ + F <= rhi && z0 + TZ <= zhi && x0 - F >= 0 &&
+                              x0 + TX + F <= nx && bz0 >= blo && bz1 + 1 < bhi && bz1 + 1 < nzc && bx0 >= 0 && bx1 + 1 < nxc &&
+                              2 * bz1 + 1 < nz && 2 * bx1 + 1 < nx;
+        if (interior) up5_tile<true>(smem, v, b, xin, xout, w, e, nzc, nxc, blo, bhi, z0, x0, rlo, rhi, acc);
+        else up5_tile<false>(smem, v, b, xin, xout, w, e, nzc, nxc, blo, bhi, z0, x0, rlo, rhi, acc);
     }
     grid_sum_finalize<2>(acc, partials, counter, [=](const double(&part)[2]) {
         double tot[1] = {part[0]};

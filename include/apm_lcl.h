@@ -165,6 +165,17 @@ APM_LCL_API int apm_lcl_run_file(const char *inp_path, int device, char *log, si
 APM_LCL_API int apm_lcl_run_file_striped(const char *inp_path, const int *devices, int n_devices, char *log,
                                          size_t log_cap);
 
+/* The statistics the reference prints next to the fields, on the device; `values` / `map` may be
+ * host or device pointers.
+ * apm_lcl_percentiles: CALC_PERCENTILE (OUTPUT_MODULE.F:53-124): out[j] = the pct[j]-th percentile of the n values in the
+ * reference's definition (sorted, duplicates collapsed, first value whose cumulative count exceeds ceil(p/100 n)), found by
+ * an exact radix select instead of a sort.
+ * apm_lcl_map_stats: MAP_STATS (MAP_MODULE.F:182-303): mean, RMS, standard deviation and the x / z correlation lengths in
+ * cells (first lag of the variogram whose semivariance passes 0.9 of the variance); any output pointer may be NULL. */
+APM_LCL_API int apm_lcl_percentiles(const double *values, size_t n, const double *pct, int npct, int device, double *out);
+APM_LCL_API int apm_lcl_map_stats(const double *map, int nx, int nz, int device, double *avg, double *rms, double *dev,
+                                  double *x_corr, double *z_corr);
+
 /* Kernel-level entry points used by the parity tests -------------------------------------- */
 
 /* COEF + FLOW_BOUNDARY: writes WIDTH[nz*nx], TRX[nz][nx+1] (faces 0..NX of each row) and

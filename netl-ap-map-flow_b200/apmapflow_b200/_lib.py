@@ -79,7 +79,7 @@ EXPORTS = (
     "apm_lcl_run_file", "apm_lcl_bulk_solve",
     "apm_lcl_peer_handle_bytes", "apm_lcl_solver_create_striped", "apm_lcl_solver_connect",
     "apm_lcl_solver_disconnect", "apm_lcl_solver_rows", "apm_lcl_solve_striped",
-    "apm_lcl_run_file_striped",
+    "apm_lcl_run_file_striped", "apm_lcl_percentiles", "apm_lcl_map_stats",
 )
 
 _lib = None
@@ -133,6 +133,8 @@ def bind(lib):
     lib.apm_lcl_run_file.restype = C.c_int
     lib.apm_lcl_run_file_striped.argtypes = [C.c_char_p, C.POINTER(C.c_int), C.c_int, C.c_char_p, C.c_size_t]
     lib.apm_lcl_run_file_striped.restype = C.c_int
+    lib.apm_lcl_percentiles.argtypes = [C.c_void_p, C.c_size_t, C.POINTER(C.c_double), C.c_int, C.c_int, C.POINTER(C.c_double)]
+    lib.apm_lcl_map_stats.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int] + [C.POINTER(C.c_double)] * 5
     return lib
 
 

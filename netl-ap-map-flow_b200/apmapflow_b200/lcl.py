@@ -301,6 +301,37 @@ def conductance(params, aperture, device=0, lib=None):
     return width, trx, trz, sc.as_dict()
 
 
+def percentiles(values, pct, device=0, lib=None):
+    """CALC_PERCENTILE (OUTPUT_MODULE.F:53-124) of a host array or CUDA tensor, on the device."""
+    lib = lib if lib is not None else _lib.load()
+    pct = np.ascontiguousarray(pct, dtype=np.float64)
+    out = np.empty(len(pct))
+    if _is_torch_cuda(values):
+        v = values.contiguous()
+        ptr, n = v.data_ptr(), v.numel()
+    else:
+        v = np.ascontiguousarray(values, dtype=np.float64)
+        ptr, n = v.ctypes.data, v.size
+    _lib_check(lib, lib.apm_lcl_percentiles(ptr, n, pct.ctypes.data_as(C.POINTER(C.c_double)), len(pct), int(device),
+                                            out.ctypes.data_as(C.POINTER(C.c_double))))
+    return out
+
+
+def map_stats(data_map, device=0, lib=None):
+    """MAP_STATS (MAP_MODULE.F:182-303): dict with avg, rms, dev and the x / z correlation lengths in cells."""
+    lib = lib if lib is not None else _lib.load()
+    if _is_torch_cuda(data_map):
+        m = data_map.contiguous()
+        ptr = m.data_ptr()
+    else:
+        m = np.ascontiguousarray(data_map, dtype=np.float64)
+        ptr = m.ctypes.data
+    nz, nx = m.shape
+    vals = [C.c_double() for _ in range(5)]
+    _lib_check(lib, lib.apm_lcl_map_stats(ptr, nx, nz, int(device), *[C.byref(v) for v in vals]))
+    return dict(zip(("avg", "rms", "dev", "x_corr", "z_corr"), [v.value for v in vals]))
+
+
 def bulk_solve(cases, devices=(0,), fields=("pressure",), lib=None):
     """Independent cases sharded over GPUs, one host thread per device (ctypes drops the GIL).
 

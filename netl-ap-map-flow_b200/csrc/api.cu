@@ -95,7 +95,7 @@ static Solver *solver_new(int device, int nx, int nz, int rank, int world, void 
         s->num_sms = prop.multiProcessorCount;
         CUDA_CHECK(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
         CUDA_CHECK(cudaStreamCreateWithFlags(&s->copy_stream, cudaStreamNonBlocking));
-        preload_conductance(); preload_flux(); preload_pcg(); preload_peer(); preload_cycle(); preload_setup();
+        preload_conductance(); preload_flux(); preload_pcg(); preload_peer(); preload_cycle(); preload_setup(); preload_stats();
         preload_one(k_side_inflow);
         mg_plan(*s);
         Arena count_pass;

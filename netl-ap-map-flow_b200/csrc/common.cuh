@@ -97,6 +97,7 @@ void preload_pcg();
 void preload_peer();
 void preload_cycle();
 void preload_setup();
+void preload_stats();
 
 inline int div_up(long long a, long long b) { return (int)((a + b - 1) / b); }
 

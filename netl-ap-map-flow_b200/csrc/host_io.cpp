@@ -22,6 +22,7 @@
 #include <functional>
 #include <mutex>
 #include <sstream>
+#include <stdexcept>
 #include <string>
 #include <thread>
 #include <vector>
@@ -748,85 +749,20 @@ bool read_data_map(Run &r)
     return true;
 }
 
-// CALC_PERCENTILE, OUTPUT_MODULE.F:53-124 (sorted, duplicates collapsed, first value whose cumulative
-// count exceeds ceil(p/100*n))
-std::vector<double> percentiles(std::vector<double> v, const std::vector<double> &pct)
+// CALC_PERCENTILE, OUTPUT_MODULE.F:53-124, and MAP_STATS, MAP_MODULE.F:182-303, run on the device (stats.cu: exact
+// radix select instead of six sorts of N doubles, variogram lags in batches of eight); a failure there fails the
+// run -- there is no host version to fall back to.
+std::vector<double> percentiles(const std::vector<double> &v, const std::vector<double> &pct, int device)
 {
-    std::sort(v.begin(), v.end());
-    const size_t n = v.size();
-    std::vector<double> res;
-    for (double pc : pct) {
-        const double kk = std::ceil(pc / 100.0 * (double)n);
-        // cumulative count of distinct values up to index i (0-based) is (last index of that value)+1
-        size_t lo = 0;
-        double val = v.back();
-        while (lo < n) {
-            size_t hi = std::upper_bound(v.begin() + lo, v.end(), v[lo]) - v.begin();
-            if ((double)hi > kk || hi == n) { val = v[lo]; break; }
-            lo = hi;
-        }
-        res.push_back(val);
-    }
+    std::vector<double> res(pct.size());
+    if (apm_lcl_percentiles(v.data(), v.size(), pct.data(), (int)pct.size(), device, res.data()))
+        throw std::runtime_error(apm_lcl_last_error());
     return res;
 }
 
-// MAP_STATS, MAP_MODULE.F:182-303 (rms, stddev, x / z correlation lengths in cells)
-void map_stats(const std::vector<double> &m, int nx, int nz, double &rms, double &dev, double &xc, double &zc)
+void map_stats(const std::vector<double> &m, int nx, int nz, int device, double &rms, double &dev, double &xc, double &zc)
 {
-    const double cells = (double)nx * nz;
-    double avg = 0;
-    for (int x = 0; x < nx; x++)
-        for (int z = 0; z < nz; z++) avg += m[(size_t)z * nx + x];
-    avg /= cells;
-    double sm = 0, sms = 0;
-    rms = 0;
-    for (size_t i = 0; i < m.size(); i++) {
-        rms += m[i] * m[i];
-        sm += m[i] - avg;
-        sms += (m[i] - avg) * (m[i] - avg);
-    }
-    sm = (sm * sm) * (1.0 / cells);
-    rms = std::sqrt(rms * (1.0 / cells));
-    const double var = (sms - sm) * (1.0 / (cells - 1));
-    dev = std::sqrt(var);
-    const int kmax = (int)((double)std::min(nx, nz) / 2.0) + 1;
-    const unsigned T = (size_t)nx * nz > (1u << 18) ? io_threads() : 1;
-    for (int dir = 0; dir < 2; dir++) {
-        double t1 = 0, t2 = 0, t3 = 0, c = 0;
-        for (int k = 1; k <= kmax; k++) {
-            // sum of squared differences at lag k; rows are split over threads, partial sums added in
-            // a fixed order (the O(N*K) variogram is the next host hotspot once the solve is fast)
-            const int zmax = dir == 0 ? nz : nz - k, xmax = dir == 0 ? nx - k : nx;
-            double cnt = zmax > 0 && xmax > 0 ? (double)zmax * (double)xmax : 0.0, ss = 0;
-            if (cnt > 0) {
-                std::vector<double> part(T, 0.0);
-                const size_t off = dir == 0 ? (size_t)k : (size_t)k * nx;
-                parallel_ranges(zmax, T, [&](long long zb, long long ze, unsigned slot) {
-                    double acc = 0;
-                    for (long long z = zb; z < ze; z++) {
-                        const double *row = &m[(size_t)z * nx];
-                        for (int x = 0; x < xmax; x++) {
-                            const double d = row[x] - row[x + off];
-                            acc += d * d;
-                        }
-                    }
-                    part[slot] = acc;
-                });
-                for (double pp : part) ss += pp;
-            }
-            if (cnt == 0) continue;
-            const double v3 = ss / cnt;
-            c = (double)k;
-            t1 = std::fabs(v3 / var - 0.90);
-            if (v3 / var > 0.90) {
-                if (t2 < t1) c = t3;
-                break;
-            }
-            t2 = t1;
-            t3 = c;
-        }
-        (dir == 0 ? xc : zc) = c;
-    }
+    if (apm_lcl_map_stats(m.data(), nx, nz, device, nullptr, &rms, &dev, &xc, &zc)) throw std::runtime_error(apm_lcl_last_error());
 }
 
 void write_percentile_table(Run &r, const std::vector<double> &pct, const std::vector<double> &val, const std::string &title,
@@ -932,12 +868,13 @@ int run(Run &r, const std::vector<int> &devices)
     timer.lap("read + parse map");
     const int nx = r.nx, nz = r.nz;
     const size_t n = (size_t)nx * nz;
+    const int dev0 = devices.empty() ? 0 : devices[0];
     r.p.voxel_size = r.units.vox;
     const double vox = r.units.vox;
     std::vector<double> perc_ap;
     if (r.percentile) {
         r.message("     CALCULATING APERTURE PERCENTILES OF MAP");
-        perc_ap = percentiles(r.ap, r.perc);
+        perc_ap = percentiles(r.ap, r.perc, dev0);
         timer.lap("aperture percentiles");
     }
     r.p.outlet_side = side_code(r.outlet_side);
@@ -974,7 +911,7 @@ int run(Run &r, const std::vector<int> &devices)
         std::vector<double> si_map(n);
         for (size_t i = 0; i < n; i++) si_map[i] = clamped[i] * vox;
         double xc, zc;
-        map_stats(si_map, nx, nz, r.aper_rms, r.aper_dev, xc, zc);
+        map_stats(si_map, nx, nz, dev0, r.aper_rms, r.aper_dev, xc, zc);
         timer.lap("map_stats");
         r.x_corr = xc * r.p.avg_factor * vox;
         r.z_corr = zc * r.p.avg_factor * vox;
@@ -1095,11 +1032,13 @@ int run(Run &r, const std::vector<int> &devices)
     r.message("     NET FLOW RATE CALCULATED: " + G(20, 9, outrate) + " " + rtrim(r.unit_out[5]));
     r.message("     MAXIMUM NET FLOW RESIDUAL: " + G(20, 9, sc.max_residual));
     if (r.percentile) {
-        auto scaled = [&](const std::vector<double> &v, double s) { std::vector<double> t(v); for (auto &e : t) e *= s; return t; };
-        write_percentile_table(r, r.perc, percentiles(scaled(qx, r.rate_conv), r.perc), "X-FLOW", rtrim(r.unit_out[5]));
-        write_percentile_table(r, r.perc, percentiles(scaled(qz, r.rate_conv), r.perc), "Z-FLOW", rtrim(r.unit_out[5]));
-        write_percentile_table(r, r.perc, percentiles(scaled(qm, r.rate_conv), r.perc), "FLOW MAGNITUDE", rtrim(r.unit_out[5]));
-        write_percentile_table(r, r.perc, percentiles(res, r.perc), "NORMALIZED RESIDUAL", "-");
+        // an order statistic of the scaled field is the scaled order statistic (the unit factor is positive and
+        // rounding is monotone): select on the SI field, convert the handful of results
+        auto scaled = [&](std::vector<double> v, double s) { for (auto &e : v) e *= s; return v; };
+        write_percentile_table(r, r.perc, scaled(percentiles(qx, r.perc, dev0), r.rate_conv), "X-FLOW", rtrim(r.unit_out[5]));
+        write_percentile_table(r, r.perc, scaled(percentiles(qz, r.perc, dev0), r.rate_conv), "Z-FLOW", rtrim(r.unit_out[5]));
+        write_percentile_table(r, r.perc, scaled(percentiles(qm, r.perc, dev0), r.rate_conv), "FLOW MAGNITUDE", rtrim(r.unit_out[5]));
+        write_percentile_table(r, r.perc, percentiles(res, r.perc, dev0), "NORMALIZED RESIDUAL", "-");
     }
     r.blank();
     timer.lap("scalars, log, percentiles");

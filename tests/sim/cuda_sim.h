@@ -143,6 +143,8 @@ inline cudaError_t cudaGetLastError() { return 0; }
 inline cudaError_t cudaGetDeviceCount(int *c) { *c = 1; return 0; }
 inline cudaError_t cudaSetDevice(int) { return 0; }
 inline cudaError_t cudaGetDeviceProperties(cudaDeviceProp *p, int) { *p = cudaDeviceProp(); return 0; }
+enum { cudaDevAttrMultiProcessorCount = 16 };
+inline cudaError_t cudaDeviceGetAttribute(int *v, int, int) { *v = cudaDeviceProp().multiProcessorCount; return 0; }
 inline cudaError_t cudaPointerGetAttributes(cudaPointerAttributes *a, const void *) { a->type = 0; return 0; }
 inline cudaError_t cudaMalloc(void **p, size_t n) { *p = std::malloc(n ? n : 1); std::memset(*p, 0xff, n); return *p ? 0 : 2; }
 inline cudaError_t cudaFree(void *p) { std::free(p); return 0; }

@@ -13,7 +13,8 @@ t0 = time.time(); pd.DataFrame(a).to_csv(os.path.join(tmp, "map.txt"), sep="\t",
 inp = ("APER-MAP: %s/map.txt\nSUMMARY-FILE: %s/log.txt\nSTAT-FILE: %s/stat.csv\nAPER-FILE: %s/aper.csv\nFLOW-FILE: %s/flow.csv\n"
        "PRESS-FILE: %s/pres.csv\nVTK-FILE: %s/data.vtk\nOVERWRITE\nINLET-PRESS: 1000 PA\nOUTLET-PRESS: 0 PA\nOUTLET-SIDE: TOP\n"
        "FLUID-DENSITY: 1000 KG/M^3\nFLUID-VISCOSITY: 1.0 CP\nMAXIMUM MAP DIMENSION: 9999\nMAP AVERAGING FACTOR: 1\nVOXEL SIZE: 10 MICRONS\n"
-       "HIGH-MASK: 100\nLOW-MASK: 0.0001\n") % ((tmp,) * 7)
+       "HIGH-MASK: 100\nLOW-MASK: 0.0001\n"
+       "CALCULATE PERCENTILES: 0,1,5,10,15,20,25,30,40,50,60,70,75,80,85,90,95,99,100\n") % ((tmp,) * 7)
 open(os.path.join(tmp, "case.inp"), "w").write(inp)
 lib = _lib.load(); buf = C.create_string_buffer(1 << 22)
 t0 = time.time(); rc = lib.apm_lcl_run_file(os.path.join(tmp, "case.inp").encode(), 0, buf, len(buf)); dt = time.time() - t0

@@ -307,8 +307,12 @@ k_smooth9(Coarse9 v, const double *__restrict__ b, const double *__restrict__ xi
         }
         cp_async_wait_all();
         __syncthreads();
-        const Cell9 c00 = staged_cell9(stage, 2 * a, 2 * c), c01 = staged_cell9(stage, 2 * a, 2 * c + 1);
-        const Cell9 c10 = staged_cell9(stage, 2 * a + 1, 2 * c), c11 = staged_cell9(stage, 2 * a + 1, 2 * c + 1);
+        Cell9 c00 = staged_cell9(stage, 2 * a, 2 * c), c01 = staged_cell9(stage, 2 * a, 2 * c + 1);
+        Cell9 c10 = staged_cell9(stage, 2 * a + 1, 2 * c), c11 = staged_cell9(stage, 2 * a + 1, 2 * c + 1);
+        // the six couplings INSIDE the block are held by both of their cells (the same staged element read twice):
+        // say so, and the compiler drops six loads and six doubles of registers
+        c01.gw = c00.ge; c10.gs = c00.gn; c11.gsw = c00.gne;
+        c11.gs = c01.gn; c10.gse = c01.gnw; c11.gw = c10.ge;
         if (PROLONG) prolong_staged9(sx, stage2, nzc, nxc, z0, x0, nz, nx);
         __syncthreads();                                 // every operand is in registers or sx: the stages are free again
         if (t + gridDim.x < ntiles) {

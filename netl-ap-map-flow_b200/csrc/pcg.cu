@@ -43,6 +43,26 @@ k_init_rhs(Fine5 v, BoundaryValues bv, double *__restrict__ r, double *__restric
 }
 
 // q = A d and d.q;  alpha = rz / d.q
+// VEC (nx even): a thread takes two neighbouring cells and moves d, the faces and q as 128-bit words
+// (LDG.E.128 / STG.E.128: half the memory instructions for the same bytes); the arithmetic per cell is the scalar
+// kernel's, term by term.
+__device__ __forceinline__ void spmv5_finish(PcgState *st, const Dist &dc, const double (&part)[1])
+{
+    double tot[1] = {part[0]};
+    dist_sum<1>(dc, tot);
+    st->dq = tot[0];
+    if (!(tot[0] > 0.0) || !(st->rz == st->rz)) {
+        // curvature lost to rounding: harmless once the residual tests have passed (floating
+        // pockets), a failure otherwise
+        if (st->res_ok) st->converged = 1; else st->failed = 1;
+        st->alpha = 0.0;
+    } else {
+        st->alpha = st->rz / tot[0];
+    }
+    st->iter += 1;
+}
+
+template <bool VEC>
 __global__ void __launch_bounds__(kBlock)
 k_spmv5(Fine5 v, const double *__restrict__ d, double *__restrict__ q, PcgState *st, double *partials,
         unsigned int *counter, Dist dc)
@@ -50,37 +70,56 @@ k_spmv5(Fine5 v, const double *__restrict__ d, double *__restrict__ q, PcgState 
     if (stopped(st)) return;
     const F5 A{v};
     const int nz = v.nz, nx = v.nx;
-    const Tiles tiles(v.zlo, v.zhi, nx);
     double acc[1] = {0.0};
-    for (long long t = blockIdx.x; t < tiles.ntiles; t += gridDim.x) {
-        int z, xx;
-        tiles.cell(t, z, xx);
-        if (z >= v.zhi || xx >= nx) continue;
-        const size_t i = (size_t)z * nx + xx;
-        const double tl = A.left(z, xx), tr = A.right(z, xx), td = A.down(z, xx), tu = A.up(z, xx);
-        const double di = d[i];
-        // difference form (boundary faces: homogeneous Dirichlet value 0)
-        double s = tl * (di - (xx > 0 ? d[i - 1] : 0.0));
-        s += tr * (di - (xx + 1 < nx ? d[i + 1] : 0.0));
-        s += td * (di - (z > 0 ? d[i - nx] : 0.0));
-        s += tu * (di - (z + 1 < nz ? d[i + nx] : 0.0));
-        q[i] = s;
-        acc[0] += di * s;
-    }
-    grid_sum_finalize<1>(acc, partials, counter, [=](const double(&part)[1]) {
-        double tot[1] = {part[0]};
-        dist_sum<1>(dc, tot);
-        st->dq = tot[0];
-        if (!(tot[0] > 0.0) || !(st->rz == st->rz)) {
-            // curvature lost to rounding: harmless once the residual tests have passed (floating
-            // pockets), a failure otherwise
-            if (st->res_ok) st->converged = 1; else st->failed = 1;
-            st->alpha = 0.0;
-        } else {
-            st->alpha = st->rz / tot[0];
+    if (VEC) {
+        const int np = nx >> 1;                       // cell pairs per row
+        const Tiles tiles(v.zlo, v.zhi, np);
+        for (long long t = blockIdx.x; t < tiles.ntiles; t += gridDim.x) {
+            int z, p;
+            tiles.cell(t, z, p);
+            if (z >= v.zhi || p >= np) continue;
+            const int x0 = 2 * p;
+            const size_t i = (size_t)z * nx + x0;
+            const double2 dc2 = *reinterpret_cast<const double2 *>(d + i);
+            const double2 tx2 = *reinterpret_cast<const double2 *>(v.tx + i);
+            const double2 tu2 = *reinterpret_cast<const double2 *>(v.tz + i);
+            const double2 td2 = z > 0 ? *reinterpret_cast<const double2 *>(v.tz + i - nx) : *reinterpret_cast<const double2 *>(v.tzb + x0);
+            const double2 dd2 = z > 0 ? *reinterpret_cast<const double2 *>(d + i - nx) : make_double2(0.0, 0.0);
+            const double2 du2 = z + 1 < nz ? *reinterpret_cast<const double2 *>(d + i + nx) : make_double2(0.0, 0.0);
+            const double tl = x0 > 0 ? v.tx[i - 1] : v.txl[z];
+            const double dl = x0 > 0 ? d[i - 1] : 0.0, dr = x0 + 2 < nx ? d[i + 2] : 0.0;
+            // difference form (boundary faces: homogeneous Dirichlet value 0)
+            double s0 = tl * (dc2.x - dl);
+            s0 += tx2.x * (dc2.x - dc2.y);
+            s0 += td2.x * (dc2.x - dd2.x);
+            s0 += tu2.x * (dc2.x - du2.x);
+            double s1 = tx2.x * (dc2.y - dc2.x);
+            s1 += tx2.y * (dc2.y - dr);
+            s1 += td2.y * (dc2.y - dd2.y);
+            s1 += tu2.y * (dc2.y - du2.y);
+            *reinterpret_cast<double2 *>(q + i) = make_double2(s0, s1);
+            acc[0] += dc2.x * s0;
+            acc[0] += dc2.y * s1;
         }
-        st->iter += 1;
-    });
+    } else {
+        const Tiles tiles(v.zlo, v.zhi, nx);
+        for (long long t = blockIdx.x; t < tiles.ntiles; t += gridDim.x) {
+            int z, xx;
+            tiles.cell(t, z, xx);
+            if (z >= v.zhi || xx >= nx) continue;
+            const size_t i = (size_t)z * nx + xx;
+            const double tl = A.left(z, xx), tr = A.right(z, xx), td = A.down(z, xx), tu = A.up(z, xx);
+            const double di = d[i];
+            // difference form (boundary faces: homogeneous Dirichlet value 0)
+            double s = tl * (di - (xx > 0 ? d[i - 1] : 0.0));
+            s += tr * (di - (xx + 1 < nx ? d[i + 1] : 0.0));
+            s += td * (di - (z > 0 ? d[i - nx] : 0.0));
+            s += tu * (di - (z + 1 < nz ? d[i + nx] : 0.0));
+            q[i] = s;
+            acc[0] += di * s;
+        }
+    }
+    grid_sum_finalize<1>(acc, partials, counter, [=](const double(&part)[1]) { spmv5_finish(st, dc, part); });
 }
 
 // x += alpha d ; r -= alpha q ; max |alpha d_i| (how far any single pressure moved) rides along
@@ -161,13 +200,27 @@ static void launch_direction(Solver &s, const double *z, int init, bool dep)
     else LAUNCH(k_direction, g1, 256, 0, s.stream, s.d + off, z + off, cnt, (const PcgState *)s.state, init);
 }
 
+static void launch_spmv(Solver &s, bool dep)
+{
+    const Fine5 v5 = s.view5();
+    const bool vec = !(s.nx & 1);   // pairs of cells as 128-bit words need rows that start on 16 bytes
+    const int g0 = grid_for(s, s.zhi - s.zlo, vec ? s.nx / 2 : s.nx, 8);
+    if (vec) {
+        if (dep) LAUNCH_DEP(k_spmv5<true>, g0, kBlock, 0, s.stream, v5, (const double *)s.d, s.q, s.state, s.red, s.red_counters, s.dist);
+        else LAUNCH(k_spmv5<true>, g0, kBlock, 0, s.stream, v5, (const double *)s.d, s.q, s.state, s.red, s.red_counters, s.dist);
+    } else {
+        if (dep) LAUNCH_DEP(k_spmv5<false>, g0, kBlock, 0, s.stream, v5, (const double *)s.d, s.q, s.state, s.red, s.red_counters, s.dist);
+        else LAUNCH(k_spmv5<false>, g0, kBlock, 0, s.stream, v5, (const double *)s.d, s.q, s.state, s.red, s.red_counters, s.dist);
+    }
+}
+
 double bench_launch_pcg(Solver &s, const std::string &name)
 {
     const Fine5 v5 = s.view5();
     const int g0 = grid_for(s, s.zhi - s.zlo, s.nx, 8), g1 = s.num_sms * 8;
     const double n = (double)s.own_cells();
     if (name == "spmv") {
-        LAUNCH(k_spmv5, g0, kBlock, 0, s.stream, v5, (const double *)s.d, s.q, s.state, s.red, s.red_counters, s.dist);
+        launch_spmv(s, false);
         return 32.0 * n;
     }
     if (name == "update") {
@@ -238,7 +291,7 @@ int pcg_solve(Solver &s, const BoundaryValues &bv, double rel_tol, int max_iter,
         return 0;
     }
     auto enqueue_iteration = [&]() {
-        LAUNCH_DEP(k_spmv5, g0, kBlock, 0, s.stream, v5, (const double *)s.d, s.q, s.state, part, cnt, s.dist);
+        launch_spmv(s, true);
         LAUNCH_DEP(k_update, g1, 256, 0, s.stream, s.own(s.x), s.own(s.r), (const double *)s.own(s.d),
                    (const double *)s.own(s.q), own, s.state, part + 4 * kMaxPartials, cnt + 5);
         mg_vcycle(s, s.r, s.z, s.q, s.state, false);
@@ -336,7 +389,8 @@ int pcg_solve(Solver &s, const BoundaryValues &bv, double rel_tol, int max_iter,
 void preload_pcg()
 {
     preload_one(k_init_rhs);
-    preload_one(k_spmv5);
+    preload_one(k_spmv5<true>);
+    preload_one(k_spmv5<false>);
     preload_one(k_update);
     preload_one(k_direction);
     preload_one(k_true_residual);

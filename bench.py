@@ -219,7 +219,8 @@ def run_reference(args, emit):
     value = cores * n * n / (ms * 1e-3) / 1e6
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "scaling": "strong" if (args.gpus > 1 and args.mode == "striped") else "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic",
             "config": {"workload": "%d independent %dx%d log-normal maps with ~20%% contact cells per step, one per "
                                    "host core (bounded sample of the 8192x8192 workload: the reference's direct D4 "
                                    "solve needs 0.34 n^3 doubles = 1.5 TB at 8192)" % (cores, n, n)},
@@ -413,7 +414,7 @@ def main():
                 "algorithmic_bytes": kern[dom]["bytes_per_cell"] * own_cells, "peak_source": peak_src, "kernels": kern}
 
     cpu = None
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:     # the CPU baseline is timed on rank 0 at N = 1 only
         cpu, _, _ = cpu_baseline(args.cpu_sample)
 
     how = ("ONE map cut into %d row strips, one per GPU (ghost rows and dot products by peer stores over NVLink)" % world

@@ -14,7 +14,7 @@ import torch.multiprocessing as mp
 
 from helpers import synth_aperture
 from apmapflow_b200 import lcl
-from apmapflow_b200._lib import Params, LEFT, TOP, BOTTOM
+from apmapflow_b200._lib import Params, LEFT, RIGHT, TOP, BOTTOM
 
 
 def params(**kw):
@@ -121,6 +121,19 @@ def test_three_ragged_strips_rate_bc(tmp_path):
     f1, s1 = single(shape, 5, pkw)
     compare(whole, allsc, f1, s1, 3)
     assert allsc[0]["outlet_rate"] == pytest.approx(1e-9, rel=1e-6)
+
+
+def test_odd_width_and_inlet_rate_on_the_left(tmp_path):
+    """Odd nx (no paired 128-bit accesses, no interior-tile fast path) and a group-node inlet on a LEFT/RIGHT pair:
+    the side flow is then a sum over every rank's rows."""
+    shape = (128, 75)
+    pkw = params(outlet_side=RIGHT, inlet_pressure=-1.0, outlet_pressure=50.0, inlet_rate=1e-9)
+    whole, allsc = run_striped(tmp_path, 2, shape, 9, pkw, min_cells=500)
+    assert allsc[0]["gather_level"] == 2
+    f1, s1 = single(shape, 9, pkw)
+    compare(whole, allsc, f1, s1, 2)
+    assert allsc[0]["outlet_rate"] == pytest.approx(1e-9, rel=1e-6)
+    assert allsc[0]["inlet_pressure"] == pytest.approx(s1["inlet_pressure"], rel=1e-9)
 
 
 def test_map_too_small_to_stripe_is_solved_whole_by_every_rank(tmp_path):

@@ -559,12 +559,12 @@ __device__ __forceinline__ void down5_tile(double *smem, const Fine5 &v, const W
         const int z = z0 + lz, xx = x0 + lx, par = (lx + FL) & 1;
         const int p = dn_pos(lz + FL, lx + FL), pl = p + (par ? -32 : 31), pr = p + (par ? -31 : 32);
         if (INT || (z >= rlo && z < rhi && xx >= 0 && xx < nx)) {
-            const double xi = sx[p];
-            double s = sb[p];
-            s -= stx[pl] * (xi - sx[pl]);
-            s -= stx[p] * (xi - sx[pr]);
-            s -= stz[p - W] * (xi - sx[p - W]);
-            s -= stz[p] * (xi - sx[p + W]);
+            // a red cell holds x = b / diag, so b - diag x vanishes (to the rounding of that one product) and what is
+            // left of b - sum t (x - x_nb) is sum t x_nb over the black neighbours: no cancellation, two loads fewer
+            double s = stx[pl] * sx[pl];
+            s += stx[p] * sx[pr];
+            s += stz[p - W] * sx[p - W];
+            s += stz[p] * sx[p + W];
             sb[p] = s;
         }
     }

@@ -231,32 +231,49 @@ __device__ __forceinline__ void stage_prolong9(double *st, const double *__restr
     }
 }
 // sx := x + P e over the framed region from the staged operands (one thread per coarse 2x2 block)
-__device__ __forceinline__ void prolong_staged9(double *sx, const double *st, int nzc, int nxc, int z0, int x0, int nz, int nx)
+// x + P e of the coarse block (bzl, bxl) of the framed region, from the staged operands into sx and into v
+__device__ __forceinline__ void prolong_block9(double *sx, const double *st, int nzc, int nxc, int z0, int x0, int nz, int nx,
+                                               int bzl, int bxl, double (&v)[4])
 {
     constexpr int W = kSmW, BW = kPrBW, EW = kPrBW + 1;
     const double *sXin = st, *sE = st + kSmH * kSmW, *sW = sE + kPrE;
-    const int bz0 = (z0 - 2) >> 1, bx0 = (x0 - 2) >> 1;
-#pragma unroll
-    for (int k = threadIdx.x; k < kPrB; k += kSmThreads) {
-        const int bzl = k / BW, bxl = k % BW;
-        const int bz = bz0 + bzl, bx = bx0 + bxl;
-        double v00 = 0.0, v01 = 0.0, v10 = 0.0, v11 = 0.0;
-        if (bz >= 0 && bx >= 0 && bz < nzc && bx < nxc) {
-            const bool xp = 2 * bx + 1 < nx, zp = 2 * bz + 1 < nz;
-            const double *ep = sE + bzl * EW + bxl;
-            const double e00 = ep[0], e01 = ep[1], e10 = ep[EW], e11 = ep[EW + 1];   // 0 beyond the coarse grid
-            const double *xi = sXin + (2 * bzl) * W + 2 * bxl;
-            v00 = xi[0] + e00;
-            if (xp) v01 = xi[1] + (sW[k] * e00 + sW[kPrB + k] * e01);
-            if (zp) v10 = xi[W] + (sW[2 * kPrB + k] * e00 + sW[3 * kPrB + k] * e10);
-            if (zp && xp)
-                v11 = xi[W + 1] + ((sW[4 * kPrB + k] * e00 + sW[5 * kPrB + k] * e01) + (sW[6 * kPrB + k] * e10 + sW[7 * kPrB + k] * e11));
-        }
-        double *p = &sx[(2 * bzl) * W + bxl];               // split rows: even column 2 bxl here, odd one W/2 further
-        p[0] = v00;
-        p[W / 2] = v01;
-        p[W] = v10;
-        p[W + W / 2] = v11;
+    const int k = bzl * BW + bxl;
+    const int bz = ((z0 - 2) >> 1) + bzl, bx = ((x0 - 2) >> 1) + bxl;
+    v[0] = v[1] = v[2] = v[3] = 0.0;
+    if (bz >= 0 && bx >= 0 && bz < nzc && bx < nxc) {
+        const bool xp = 2 * bx + 1 < nx, zp = 2 * bz + 1 < nz;
+        const double *ep = sE + bzl * EW + bxl;
+        const double e00 = ep[0], e01 = ep[1], e10 = ep[EW], e11 = ep[EW + 1];   // 0 beyond the coarse grid
+        const double *xi = sXin + (2 * bzl) * W + 2 * bxl;
+        v[0] = xi[0] + e00;
+        if (xp) v[1] = xi[1] + (sW[k] * e00 + sW[kPrB + k] * e01);
+        if (zp) v[2] = xi[W] + (sW[2 * kPrB + k] * e00 + sW[3 * kPrB + k] * e10);
+        if (zp && xp)
+            v[3] = xi[W + 1] + ((sW[4 * kPrB + k] * e00 + sW[5 * kPrB + k] * e01) + (sW[6 * kPrB + k] * e10 + sW[7 * kPrB + k] * e11));
+    }
+    double *p = &sx[(2 * bzl) * W + bxl];               // split rows: even column 2 bxl here, odd one W/2 further
+    p[0] = v[0];
+    p[W / 2] = v[1];
+    p[W] = v[2];
+    p[W + W / 2] = v[3];
+}
+// sx := x + P e over the framed region.  Thread (a, c) builds the block it will smooth -- framed block (a + 1, c + 1) --
+// and keeps the four values (own); the 84 blocks of the frame ring are dealt to the first 84 threads.
+__device__ __forceinline__ void prolong_staged9(double *sx, const double *st, int nzc, int nxc, int z0, int x0, int nz, int nx,
+                                                double (&own)[4])
+{
+    constexpr int BH = kPrBH, BW = kPrBW;
+    static_assert((BH - 2) * (BW - 2) == kSmThreads, "one tile block per thread");
+    const int tid = threadIdx.x;
+    prolong_block9(sx, st, nzc, nxc, z0, x0, nz, nx, (tid >> 5) + 1, (tid & 31) + 1, own);
+    constexpr int kRing = BH * BW - (BH - 2) * (BW - 2);
+    if (tid < kRing) {
+        int bzl, bxl;
+        if (tid < BW) { bzl = 0; bxl = tid; }
+        else if (tid < 2 * BW) { bzl = BH - 1; bxl = tid - BW; }
+        else { bzl = 1 + ((tid - 2 * BW) >> 1); bxl = ((tid - 2 * BW) & 1) ? BW - 1 : 0; }
+        double ring[4];
+        prolong_block9(sx, st, nzc, nxc, z0, x0, nz, nx, bzl, bxl, ring);
     }
 }
 
@@ -313,7 +330,8 @@ k_smooth9(Coarse9 v, const double *__restrict__ b, const double *__restrict__ xi
         // say so, and the compiler drops six loads and six doubles of registers
         c01.gw = c00.ge; c10.gs = c00.gn; c11.gsw = c00.gne;
         c11.gs = c01.gn; c10.gse = c01.gnw; c11.gw = c10.ge;
-        if (PROLONG) prolong_staged9(sx, stage2, nzc, nxc, z0, x0, nz, nx);
+        double own[4] = {0.0, 0.0, 0.0, 0.0};
+        if (PROLONG) prolong_staged9(sx, stage2, nzc, nxc, z0, x0, nz, nx, own);
         __syncthreads();                                 // every operand is in registers or sx: the stages are free again
         if (t + gridDim.x < ntiles) {
             const long long tn = t + gridDim.x;
@@ -324,7 +342,11 @@ k_smooth9(Coarse9 v, const double *__restrict__ b, const double *__restrict__ xi
         // the thread's block: framed rows 2a+2, 2a+3, columns 2c+2 (even, half index c+1) and 2c+3 (odd)
         double *pe0 = &sx[(2 * a + 2) * W + c + 1];      // even column
         double *po0 = pe0 + W / 2;                       // odd column; west of the even one: po0 - 1, east of the odd one: pe0 + 1
-        double x00 = pe0[0], x01 = po0[0], x10 = pe0[W], x11 = po0[W];   // the block's own iterates stay in registers
+        // the block's own iterates stay in registers (the up leg has just built them, the zero guess is zero)
+        double x00, x01, x10, x11;
+        if (PROLONG) { x00 = own[0]; x01 = own[1]; x10 = own[2]; x11 = own[3]; }
+        else if (ZERO_INIT) { x00 = x01 = x10 = x11 = 0.0; }
+        else { x00 = pe0[0]; x01 = po0[0]; x10 = pe0[W]; x11 = po0[W]; }
         int sweep = 0;
         if (ZERO_INIT && nu > 0) {
             // first forward sweep from x = 0: every value a colour has not reached yet is still 0 (the frame too), and

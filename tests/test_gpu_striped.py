@@ -178,3 +178,50 @@ def test_run_model_with_devices_writes_the_same_files(tmp_path, monkeypatch):
         a = np.loadtxt(outs["one"] / name, delimiter=",")
         b = np.loadtxt(outs["striped"] / name, delimiter=",")
         assert np.abs(a - b).max() <= 1e-6 * np.abs(a).max(), name
+
+
+def test_config3_full_size_8192_strips_equal_the_single_solve():
+    """BASELINE config 3 at full size: the 8192^2 map with 20 % contact cells, cut into 2 and into 4 row strips (all on
+    GPU 0: the striped code path, not the scaling), against the single-GPU solve of the same map; plus the
+    size-independent properties: both residual norms met, inflow == outflow, determinism."""
+    import torch
+    sys.path.insert(0, ROOT)
+    import bench
+    n = 8192
+    dev = torch.device("cuda", 0)
+    a = bench.synth_map_torch(n, 0, dev)
+    p = bench.synth_params()
+    with lcl.LclSolver(n, n) as solver:
+        f1, s1 = solver.solve(p, a, fields=("pressure", "flow_z"))
+        f1b, _ = solver.solve(p, a, fields=("pressure",))
+        assert torch.equal(f1["pressure"], f1b["pressure"])                        # deterministic
+        tz, _ = _dev_array(solver, "tz", n * n)
+        tzb, _ = _dev_array(solver, "tzb", n)
+        q_in = float((tzb * (1000.0 - f1["pressure"][0])).sum())
+        q_out = float((tz.view(n, n)[-1] * (f1["pressure"][-1] - 0.0)).sum())
+    assert s1["converged"] == 1 and s1["rel_residual"] <= 1e-10 and s1["rel_residual_scaled"] <= 1e-10
+    assert q_in == pytest.approx(q_out, rel=1e-7) and abs(s1["flow"]) == pytest.approx(q_out, rel=1e-6)
+    assert s1["iterations"] <= 16                                                   # 13 measured
+    a_host = a.cpu().numpy()
+    ref = f1["pressure"].cpu().numpy()
+    del f1, f1b, a
+    torch.cuda.empty_cache()
+    for world in (2, 4):
+        whole, s = lcl.lcl_solve_striped(p, a_host, [0] * world, fields=("pressure",))
+        assert s["converged"] == 1 and abs(s["iterations"] - s1["iterations"]) <= 1
+        assert s["flow"] == pytest.approx(s1["flow"], rel=1e-9)
+        assert np.abs(whole["pressure"] - ref).max() <= 2e-7 * 1000.0
+        assert (s["zeros"], s["masked"]) == (s1["zeros"], s1["masked"])
+
+
+def _dev_array(solver, name, count):
+    import ctypes as C
+    import torch
+    ptr, cnt = C.c_void_p(), C.c_size_t()
+    assert solver.lib.apm_lcl_solver_device_field(solver._h, name.encode(), C.byref(ptr), C.byref(cnt)) == 0
+    assert cnt.value == count
+    out = torch.empty(count, dtype=torch.float64, device="cuda:0")
+    from cuda.bindings import runtime as cudart
+    (err,) = cudart.cudaMemcpy(out.data_ptr(), ptr.value, count * 8, cudart.cudaMemcpyKind.cudaMemcpyDeviceToDevice)
+    assert int(err) == 0
+    return out, cnt.value

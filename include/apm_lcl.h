@@ -52,8 +52,11 @@ typedef struct apm_lcl_params {
     /* solver controls (new; the reference's direct D4 solve has none) */
     double rel_tol;          /* stop when ||r||2/||b||2 AND ||D^-1/2 r||/||D^-1/2 b|| <= rel_tol; <=0 -> 1e-10 */
     int    max_iter;         /* <=0 -> 500                                              */
-    int    flags;            /* reserved, 0                                             */
+    int    flags;            /* APM_LCL_FLAG_* bits, 0 by default                       */
 } apm_lcl_params;
+
+/* apm_lcl_bulk_solve: never derive this case from another case's unit solution (see there) */
+#define APM_LCL_FLAG_OWN_SOLVE 1
 
 /* Per-cell outputs, SI units, each nz*nx doubles or NULL to skip (host or device pointers).
  * APERTURE_MAP_FLOW.F:825-869 before the output-unit conversion. */
@@ -145,7 +148,11 @@ APM_LCL_API int apm_lcl_solve(const apm_lcl_params *p, const double *aperture, i
 /* Many independent cases of one map size on one device (the tensor-level counterpart of
  * BulkRun, apmapflow/run_model/bulk_run.py:107-128: independent simulations, no exchange between
  * them).  Case k uses params[k], apertures[k] and writes outs[k] / scalars[k]; one solver object is
- * reused, so allocations, the CUDA graph and the multigrid storage are paid once.  Returns the number
+ * reused, so allocations, the CUDA graph and the multigrid storage are paid once.  Cases that pass the SAME
+ * aperture pointer and differ only in inlet_pressure / outlet_pressure (both supplied, no rates: a sweep over
+ * OUTLET-PRESS) share one unit solution, p = OUTPB + (INLPB - OUTPB) u: the first is solved, the others are an
+ * affine map of its pressure field plus the flux pass and report iterations = 0.  APM_LCL_BULK_SHARE=0 in the
+ * environment, or APM_LCL_FLAG_OWN_SOLVE in a case's params.flags, solves every case on its own.  Returns the number
  * of failed cases (0 = all good); a failed case has scalars[k].converged == 0 and the last message in
  * apm_lcl_last_error().  Shard the case list over GPUs by calling this once per device from one
  * thread/process per device (apmapflow_b200.lcl.bulk_solve does that). */

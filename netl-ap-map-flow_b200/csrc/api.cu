@@ -4,6 +4,7 @@
 // OUTPUT_DATA sequence (apmapflow/src/APERTURE_MAP_FLOW.F:28-42), restricted to its numeric core.
 #include <cmath>
 #include <cstdlib>
+#include <algorithm>
 #include <atomic>
 #include <cstring>
 #include <mutex>
@@ -226,7 +227,35 @@ static void read_map_scalars(Solver &s, const apm_lcl_params &p, apm_lcl_scalars
     sc->max_aper = s.scal_host[SC_MAX];
 }
 
-static void do_solve(Solver &s, const apm_lcl_params &p, const double *aperture, apm_lcl_fields *out, apm_lcl_scalars *sc)
+static bool pressure_controlled(const apm_lcl_params &p)
+{
+    return p.inlet_pressure >= 0 && p.outlet_pressure >= 0 && !(p.inlet_rate > 0) && !(p.outlet_rate > 0);
+}
+
+// Two pressure-controlled cases of the SAME map that differ in nothing but the two boundary pressures have the same
+// unit solution u (inlet side 1, outlet side 0): p = OUTPB + (INLPB - OUTPB) u.
+static bool same_unit_problem(const apm_lcl_params &a, const apm_lcl_params &b)
+{
+    return pressure_controlled(a) && pressure_controlled(b) && a.density == b.density && a.viscosity == b.viscosity &&
+           a.voxel_size == b.voxel_size && a.avg_factor == b.avg_factor && a.roughness == b.roughness &&
+           a.high_mask == b.high_mask && a.low_mask == b.low_mask && a.outlet_side == b.outlet_side &&
+           a.rel_tol == b.rel_tol && a.max_iter == b.max_iter && a.flags == b.flags;
+}
+
+// The pressure field of the last solve gives u back as (p - OUTPB') / (INLPB' - OUTPB'), to eps max|p'| / |drop'|:
+// only a previous case whose drop is not tiny against its pressures may be rescaled (1e-12 on u per link).
+static bool unit_solution_recoverable(const Solver &s)
+{
+    if (!s.have_solution || !pressure_controlled(s.last_params)) return false;
+    const double drop = std::fabs(s.last_params.inlet_pressure - s.last_params.outlet_pressure);
+    return std::max(s.last_params.inlet_pressure, s.last_params.outlet_pressure) <= 1e4 * drop;
+}
+
+// `same_map`: the caller guarantees that `aperture` holds the map of this solver's previous solve (apm_lcl_bulk_solve:
+// the same pointer inside one call).  Then a case that only changes the boundary pressures is an affine map of the
+// pressure field already in s.x followed by the flux pass -- no conductances, no hierarchy, no PCG.
+static void do_solve(Solver &s, const apm_lcl_params &p, const double *aperture, apm_lcl_fields *out, apm_lcl_scalars *sc,
+                     bool same_map = false)
 {
     validate(p);
     if (!s.connected) throw CudaError{"striped solver is not connected to its peers (apm_lcl_solver_connect)"};
@@ -238,10 +267,16 @@ static void do_solve(Solver &s, const apm_lcl_params &p, const double *aperture,
     if (!sc) sc = &local;
     std::memset(sc, 0, sizeof(*sc));
     const size_t own_off = (size_t)s.zlo * s.nx;
+    const bool reuse = same_map && s.have_hierarchy && s.world == 1 && same_unit_problem(p, s.last_params) &&
+                       unit_solution_recoverable(s);
+    const apm_lcl_params prev = s.last_params;
+    const apm_lcl_scalars prev_sc = s.last_scalars;
+    s.have_solution = false;   // until this solve has come through
+    if (!reuse) s.have_hierarchy = false;
 
-    const double *ap_dev = stage_aperture(s, aperture);
+    const double *ap_dev = reuse ? s.ap : stage_aperture(s, aperture);
     CUDA_CHECK(cudaEventRecord(s.ev[0], s.stream));
-    launch_conductance(s, p, ap_dev);
+    if (!reuse) launch_conductance(s, p, ap_dev);
     // WIDTH is final here: a host caller gets it over a second stream while the solve runs (PCIe is idle
     // until the other fields exist); the guard makes sure the copy has landed on every way out
     struct CopyGuard {
@@ -249,14 +284,14 @@ static void do_solve(Solver &s, const apm_lcl_params &p, const double *aperture,
         bool active = false;
         ~CopyGuard() { if (active) cudaStreamSynchronize(st); }
     } early{s.copy_stream};
-    if (out && out->aperture && !is_device_ptr(out->aperture)) {
+    if (!reuse && out && out->aperture && !is_device_ptr(out->aperture)) {
         CUDA_CHECK(cudaEventRecord(s.ev[5], s.stream));
         CUDA_CHECK(cudaStreamWaitEvent(s.copy_stream, s.ev[5], 0));
         CUDA_CHECK(cudaMemcpyAsync(out->aperture, s.width + own_off, s.own_cells() * sizeof(double), cudaMemcpyDeviceToHost,
                                    s.copy_stream));
         early.active = true;
     }
-    mg_setup(s);
+    if (!reuse) mg_setup(s);
     CUDA_CHECK(cudaEventRecord(s.ev[1], s.stream));
 
     // boundary-condition mode (APERTURE_MAP_FLOW.F:137-143, 644-659)
@@ -265,7 +300,15 @@ static void do_solve(Solver &s, const apm_lcl_params &p, const double *aperture,
     double inl = p.inlet_pressure, outp = p.outlet_pressure;
     const int side = p.outlet_side, in_side = opposite(side);
     int rc_iters = 0;
-    if (has_in && has_out && !rate_in && !rate_out) {
+    if (reuse) {
+        // s.x = OUTPB' + drop' u  ->  OUTPB + drop u
+        const double scale = (inl - outp) / (prev.inlet_pressure - prev.outlet_pressure);
+        launch_affine(s, s.own(s.x), s.own_cells(), scale, outp - scale * prev.outlet_pressure);
+        sc->iterations = 0;   // none of its own: the unit solution is the earlier case's
+        sc->converged = prev_sc.converged;
+        sc->rel_residual = prev_sc.rel_residual;
+        sc->rel_residual_scaled = prev_sc.rel_residual_scaled;
+    } else if (has_in && has_out && !rate_in && !rate_out) {
         // Solved as the unit problem u (inlet side 1, outlet side 0) and p = OUTPB + (INLPB - OUTPB) u:
         // right-hand side, both residual norms and the pointwise stagnation test then scale with the pressure
         // DROP.  Solving for absolute pressures makes them scale with |P|, and the fluxes -- differences of
@@ -318,7 +361,7 @@ static void do_solve(Solver &s, const apm_lcl_params &p, const double *aperture,
     for (int k = 0; k < 5; k++)
         *slot[k] = user[k] ? (is_device_ptr(user[k]) ? user[k] - own_off : scratch[k]) : nullptr;
     // s.ap doubles as the residual scratch: the staged copy of the map is dead after the conductance pass
-    s.ap_valid = ap_dev == s.ap && fo.res != s.ap;
+    s.ap_valid = !reuse && ap_dev == s.ap && fo.res != s.ap;
     launch_flux(s, p, s.x, bvf, fo);
     CUDA_CHECK(cudaEventRecord(s.ev[3], s.stream));
     for (int k = 0; k < 5; k++) copy_out(s, user[k], *slot[k]);
@@ -336,9 +379,10 @@ static void do_solve(Solver &s, const apm_lcl_params &p, const double *aperture,
     CUDA_CHECK(cudaEventElapsedTime(&ms, s.ev[0], s.ev[1])); sc->setup_ms = ms;
     CUDA_CHECK(cudaEventElapsedTime(&ms, s.ev[1], s.ev[2])); sc->solve_ms = ms;
     CUDA_CHECK(cudaEventElapsedTime(&ms, s.ev[0], s.ev[4])); sc->total_ms = ms;
-    s.have_solution = true;
+    s.have_solution = sc->converged != 0;
     s.have_hierarchy = true;
     s.last_params = p;
+    s.last_scalars = *sc;
     if (!sc->converged) {
         char buf[256];
         snprintf(buf, sizeof buf, "PCG did not reach rel_tol %.3g in %d iterations (residual %.3e, scaled %.3e)",
@@ -571,34 +615,69 @@ int apm_lcl_bulk_solve(int device, int nx, int nz, int n_cases, const apm_lcl_pa
 #ifdef LCL_CPU_SIM
     workers = 1;   // the test-only CPU emulation of the kernels is single threaded
 #endif
+    // Cases of one call that pass the SAME aperture pointer and differ only in the two boundary pressures (a BulkRun
+    // sweep over OUTLET-PRESS, bulk_run.py:208-234) share one unit solution: the first of them is solved, the others are
+    // an affine map of its pressure field plus the flux pass (do_solve(same_map)).  Such cases form a group that one
+    // worker takes as a whole; everything else is a group of one.  APM_LCL_BULK_SHARE=0 solves every case on its own
+    // (the number bench / tools report as the honest one), as does bit 0 of params.flags for that case.
+    bool share = true;
+    if (const char *e = getenv("APM_LCL_BULK_SHARE")) share = atoi(e) != 0;
+    std::vector<std::vector<int>> groups;
+    for (int k = 0; k < n_cases; k++) {
+        bool placed = false;
+        if (share && !(params[k].flags & APM_LCL_FLAG_OWN_SOLVE) && pressure_controlled(params[k]))
+            for (auto &g : groups)
+                if (apertures[g[0]] == apertures[k] && !(params[g[0]].flags & APM_LCL_FLAG_OWN_SOLVE) &&
+                    same_unit_problem(params[g[0]], params[k])) {
+                    g.push_back(k);
+                    placed = true;
+                    break;
+                }
+        if (!placed) groups.push_back({k});
+    }
+    const int n_groups = (int)groups.size();
+    if (workers > n_groups) workers = n_groups;
     std::atomic<int> next{0}, failed{0};
     std::atomic<long long> launches{0};
     std::mutex err_mutex;
     std::string first_error;
     int first_error_case = n_cases;
+    auto fail = [&](int k, const std::string &msg) {
+        if (scalars) scalars[k].converged = 0;
+        failed++;
+        std::lock_guard<std::mutex> lock(err_mutex);
+        if (k < first_error_case) { first_error_case = k; first_error = msg; }
+    };
     auto work = [&]() {
         apm_lcl_solver *h = nullptr;
         if (apm_lcl_solver_create(&h, device, nx, nz)) {
             // no solver: every case this worker would have taken fails
             const std::string msg = g_last_error;
-            for (int k = next.fetch_add(1); k < n_cases; k = next.fetch_add(1)) {
-                if (scalars) scalars[k].converged = 0;
-                failed++;
-                std::lock_guard<std::mutex> lock(err_mutex);
-                if (k < first_error_case) { first_error_case = k; first_error = msg; }
-            }
+            for (int g = next.fetch_add(1); g < n_groups; g = next.fetch_add(1))
+                for (int k : groups[g]) fail(k, msg);
             return;
         }
-        for (int k = next.fetch_add(1); k < n_cases; k = next.fetch_add(1)) {
-            apm_lcl_scalars local{};
-            apm_lcl_scalars *sc = scalars ? &scalars[k] : &local;
-            if (apm_lcl_solver_solve(h, &params[k], apertures[k], outs ? &outs[k] : nullptr, sc)) {
-                failed++;
-                sc->converged = 0;
-                std::lock_guard<std::mutex> lock(err_mutex);
-                if (k < first_error_case) { first_error_case = k; first_error = g_last_error; }
+        for (int g = next.fetch_add(1); g < n_groups; g = next.fetch_add(1)) {
+            bool have_first = false;
+            for (int k : groups[g]) {
+                apm_lcl_scalars local{};
+                apm_lcl_scalars *sc = scalars ? &scalars[k] : &local;
+                int rc = 1;
+                try {
+                    do_solve(*h->s, params[k], apertures[k], outs ? &outs[k] : nullptr, sc, have_first);
+                    rc = 0;
+                } catch (const CudaError &e) {
+                    g_last_error = e.msg;
+                } catch (const std::exception &e) {
+                    g_last_error = e.what();
+                }
+                if (rc) {
+                    sc->converged = 0;
+                    fail(k, g_last_error);
+                }
+                have_first = rc == 0;    // after a failure the next case of the group is solved in full
+                launches += g_launches;
             }
-            launches += g_launches;
         }
         apm_lcl_solver_destroy(h);
     };

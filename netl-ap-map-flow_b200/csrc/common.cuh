@@ -278,6 +278,7 @@ struct Solver {
     bool ap_valid = false;         // ap holds the staged aperture map of the last solve (not flux scratch)
     bool down_configured = false;   // k_down5 opted in to >48 KB dynamic shared memory on this device
     apm_lcl_params last_params{};
+    apm_lcl_scalars last_scalars{};
     Fine5 view5() const { return Fine5{tx, tz, txl, tzb, nz, nx, zlo, zhi}; }
     size_t own_cells() const { return (size_t)(zhi - zlo) * nx; }
     double *own(double *p) const { return p + (size_t)zlo * nx; }   // first owned element of a fine-level array

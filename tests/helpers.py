@@ -113,3 +113,60 @@ def anchored_open_mask(a, low_mask=0.0, vertical_flow=True):
         edge = set(np.unique(lab[:, 0])) | set(np.unique(lab[:, -1]))
     edge.discard(0)
     return np.isin(lab, list(edge))
+
+
+def check_bulk_sweep_shares_unit_solutions(lcl, lib, params_of, monkeypatch, shape=(40, 36), full=True):
+    """BASELINE config 5 in miniature: maps x boundary pressures through apm_lcl_bulk_solve.  Cases of one map that
+    differ only in the boundary pressures are derived from ONE unit solve (iterations == 0 for the derived ones) and
+    must agree with their own full solves; APM_LCL_BULK_SHARE=0 / the OWN_SOLVE flag solve every case bit-identically
+    to single solves.  ``params_of(**kw)`` builds a Params."""
+    import numpy as np
+    import pytest
+    maps = [synth_aperture(shape[0], shape[1], seed=k, sigma_c=3, contact=0.1, sigma_k=5) for k in range(2)]
+    sweep = [(1000.0, 0.0), (1000.0, 937.5), (2.0e5 + 50.0, 2.0e5), (1000.0, 250.0)][:4 if full else 3]
+    ns = len(sweep)
+    cases = [(params_of(inlet_pressure=pi, outlet_pressure=po), m) for m in maps for pi, po in sweep]
+    # a rate-controlled case and a case with another viscosity on the first map: never derived
+    cases.append((params_of(inlet_pressure=-1.0, outlet_pressure=0.0, inlet_rate=1e-9), maps[0]))
+    if full:
+        cases.append((params_of(inlet_pressure=1000.0, outlet_pressure=0.0, viscosity=2e-3), maps[0]))
+    fields = ("pressure", "flow_x", "flow_z", "residual", "aperture")
+    singles = [lcl.lcl_solve(p, m, fields=fields, lib=lib) for p, m in cases]
+
+    monkeypatch.delenv("APM_LCL_BULK_SHARE", raising=False)
+    shared = lcl.bulk_solve(cases, devices=(0,), fields=fields, lib=lib)
+    derived = [k for k, (_, sc) in enumerate(shared) if sc["iterations"] == 0]
+    assert derived == [k for k in range(2 * ns) if k % ns]                       # first case of each map is the one that is solved
+    for k, ((p, m), (arr, sc), (f, s)) in enumerate(zip(cases, shared, singles)):
+        assert sc["converged"] == 1 and sc["outlet_pressure"] == s["outlet_pressure"]
+        drop = s["inlet_pressure"] - s["outlet_pressure"]
+        if k in derived:
+            assert np.abs(arr["pressure"] - f["pressure"]).max() <= 1e-9 * drop + 4e-16 * s["inlet_pressure"]
+            assert sc["flow"] == pytest.approx(s["flow"], rel=1e-8)
+            qm = np.abs(f["flow_z"]).max()
+            # the stored pressures carry eps * |p| each: the floor of a flux out of absolute pressures
+            floor = 8 * np.finfo(float).eps * s["inlet_pressure"] / (drop / shape[0])
+            assert np.abs(arr["flow_z"] - f["flow_z"]).max() <= (1e-8 + floor) * qm
+            assert np.abs(arr["flow_x"] - f["flow_x"]).max() <= (1e-8 + floor) * qm
+            assert (sc["zeros"], sc["masked"], sc["avg_aper"]) == (s["zeros"], s["masked"], s["avg_aper"])
+        else:
+            assert sc["iterations"] == s["iterations"] > 0
+            for name in fields:
+                assert np.array_equal(arr[name], f[name], equal_nan=True), (k, name)
+        assert np.array_equal(arr["aperture"], f["aperture"])
+
+    monkeypatch.setenv("APM_LCL_BULK_SHARE", "0")
+    own = lcl.bulk_solve(cases if full else cases[:3], devices=(0,), fields=fields, lib=lib)
+    for (arr, sc), (f, s) in zip(own, singles):
+        assert sc["iterations"] == s["iterations"] > 0 and sc["flow"] == s["flow"]
+        assert all(np.array_equal(arr[name], f[name], equal_nan=True) for name in fields)
+    monkeypatch.delenv("APM_LCL_BULK_SHARE")
+    if not full:
+        return
+    flagged = []
+    for p, m in cases[:4]:
+        q = type(p).from_buffer_copy(p)
+        q.flags = 1                                            # APM_LCL_FLAG_OWN_SOLVE
+        flagged.append((q, m))
+    for (arr, sc), (f, s) in zip(lcl.bulk_solve(flagged, devices=(0,), fields=fields, lib=lib), singles):
+        assert sc["iterations"] == s["iterations"] > 0 and np.array_equal(arr["pressure"], f["pressure"])

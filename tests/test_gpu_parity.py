@@ -203,19 +203,26 @@ def test_torch_cuda_tensor_io_matches_host_io():
     assert s_dev["flow"] == s_host["flow"]
 
 
-def test_bulk_solve_matches_single_solves():
-    """BASELINE config 5 in miniature: (map, outlet pressure) sweep through apm_lcl_bulk_solve."""
+def test_bulk_solve_matches_single_solves(monkeypatch):
+    """BASELINE config 5 in miniature: (map, outlet pressure) sweep through apm_lcl_bulk_solve, every case solved
+    on its own (the sharing of unit solutions is the next test)."""
+    monkeypatch.setenv("APM_LCL_BULK_SHARE", "0")
     maps = [synth_aperture(96, 128, seed=k, sigma_c=4, contact=0.1, sigma_k=6) for k in range(3)]
     cases = [(synth_params(outlet_pressure=p_out), m) for m in maps for p_out in (0.0, 250.0, 937.5)]
     res = lcl.bulk_solve(cases, devices=(0,), fields=("pressure", "flow_z"))
     assert len(res) == 9
     for (p, m), (arr, sc) in zip(cases, res):
         f, s = lcl.lcl_solve(p, m, fields=("pressure", "flow_z"))
-        assert sc["converged"] == 1 and sc["outlet_pressure"] == p.outlet_pressure
+        assert sc["converged"] == 1 and sc["outlet_pressure"] == p.outlet_pressure and sc["iterations"] > 0
         assert np.array_equal(arr["pressure"], f["pressure"]) and sc["flow"] == s["flow"]
     # affine in the boundary pressures: flow scales with (P_in - P_out) on the same map
     q0, q1 = res[0][1]["flow"], res[1][1]["flow"]
     assert q1 / q0 == pytest.approx(750.0 / 1000.0, rel=1e-6)
+
+
+def test_bulk_sweep_shares_unit_solutions(monkeypatch):
+    from helpers import check_bulk_sweep_shares_unit_solutions
+    check_bulk_sweep_shares_unit_solutions(lcl, None, lambda **k: synth_params(**k), monkeypatch, shape=(300, 260))
 
 
 def _device_vector(solver, name):

@@ -113,6 +113,12 @@ def test_sim_back_pressure_does_not_cost_flux_accuracy(sim, base):
     assert np.abs((f1["pressure"] - base) - f0["pressure"]).max() <= (1e-6 + floor) * 100.0
 
 
+def test_sim_bulk_sweep_shares_unit_solutions(sim, monkeypatch):
+    from helpers import check_bulk_sweep_shares_unit_solutions
+    kw = dict(voxel_size=1e-5, avg_factor=1.0, viscosity=1e-3)
+    check_bulk_sweep_shares_unit_solutions(lcl, sim, lambda **k: params(**dict(kw, **k)), monkeypatch, shape=(20, 18), full=False)
+
+
 def test_sim_invalid_boundary_conditions_fail(sim):
     a = synth_aperture(8, 8, seed=1, sigma_c=0)
     with pytest.raises(lcl._lib.LclError):

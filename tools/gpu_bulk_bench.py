@@ -1,5 +1,7 @@
 """GPU helper (run under gpurun): BASELINE config 5 -- 16 maps x 16 outlet pressures at 1024^2 through
-apm_lcl_bulk_solve -- timed for several numbers of concurrent solvers per device."""
+apm_lcl_bulk_solve -- timed for several numbers of concurrent solvers per device, every case solved on its own
+(APM_LCL_BULK_SHARE=0: the honest 256-solve number), then with the cases of one map sharing their unit solution
+(the library's default: 16 solves + 240 affine maps and flux passes; reported separately)."""
 import os, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 for p in (ROOT, os.path.join(ROOT, "netl-ap-map-flow_b200"), os.path.join(ROOT, "tests")):
@@ -19,11 +21,14 @@ for m in maps:
                                       voxel_size=1e-5, avg_factor=1.0, roughness=0.0, high_mask=100.0, low_mask=1e-4,
                                       outlet_side=TOP), m))
 lcl.bulk_solve(cases[:8], devices=(0,))          # warm-up (context, module load)
-for streams in (1, 2, 4, 8):
-    os.environ["APM_LCL_BULK_STREAMS"] = str(streams)
-    t0 = time.time()
-    res = lcl.bulk_solve(cases, devices=(0,), fields=("pressure",))
-    dt = time.time() - t0
-    ok = all(s["converged"] == 1 for _, s in res)
-    print("n=%d cases=%d streams=%d wall=%.3f s  %.2f ms/case  %.1f Mcells/s  all converged=%s" %
-          (n, len(cases), streams, dt, 1e3 * dt / len(cases), len(cases) * n * n / dt / 1e6, ok), flush=True)
+for share, stream_counts in (("0", (1, 2, 4, 8)), ("1", (1, 4))):
+    os.environ["APM_LCL_BULK_SHARE"] = share
+    for streams in stream_counts:
+        os.environ["APM_LCL_BULK_STREAMS"] = str(streams)
+        t0 = time.time()
+        res = lcl.bulk_solve(cases, devices=(0,), fields=("pressure",))
+        dt = time.time() - t0
+        ok = all(s["converged"] == 1 for _, s in res)
+        solved = sum(s["iterations"] > 0 for _, s in res)
+        print("n=%d cases=%d (PCG solves: %d) share=%s streams=%d wall=%.3f s  %.2f ms/case  %.1f Mcells/s  all converged=%s" %
+              (n, len(cases), solved, share, streams, dt, 1e3 * dt / len(cases), len(cases) * n * n / dt / 1e6, ok), flush=True)

@@ -14,6 +14,12 @@ from ._lib import Fields, Params, Scalars
 FIELD_NAMES = ("pressure", "flow_x", "flow_z", "flow_m", "aperture", "reynolds", "residual")
 
 
+def _check_shape(shape, expected):
+    """A wrong shape would make the library read past the buffer: refuse it here (not an assert, those vanish with -O)."""
+    if tuple(shape) != tuple(expected):
+        raise ValueError("aperture map has shape %s, the solver was created for %s" % (tuple(shape), tuple(expected)))
+
+
 def _is_torch_cuda(a):
     return type(a).__module__.startswith("torch") and getattr(a, "is_cuda", False)
 
@@ -53,7 +59,7 @@ class LclSolver(object):
         if _is_torch_cuda(aperture):
             import torch
             a = aperture.to(torch.float64).contiguous()
-            assert tuple(a.shape) == (self.nz, self.nx)
+            _check_shape(a.shape, (self.nz, self.nx))
             ptr = a.data_ptr()
             for name in fields:
                 arrays[name] = torch.empty_like(a)
@@ -61,7 +67,7 @@ class LclSolver(object):
             torch.cuda.current_stream(a.device).synchronize()   # inputs complete before our stream reads
         else:
             a = np.ascontiguousarray(aperture, dtype=np.float64)
-            assert a.shape == (self.nz, self.nx)
+            _check_shape(a.shape, (self.nz, self.nx))
             ptr = a.ctypes.data
             for name in fields:
                 arrays[name] = np.empty((self.nz, self.nx))
@@ -147,7 +153,7 @@ class StripedLclSolver(object):
         rows_in, rows_out = self.a_hi - self.a_lo, self.z_hi - self.z_lo
         if aperture.shape[0] == self.nz and rows_in != self.nz:
             aperture = aperture[self.a_lo:self.a_hi]
-        assert tuple(aperture.shape) == (rows_in, self.nx), (tuple(aperture.shape), rows_in, self.nx)
+        _check_shape(aperture.shape, (rows_in, self.nx))
         out = Fields()
         arrays = {}
         if _is_torch_cuda(aperture):
@@ -236,7 +242,7 @@ class StripedGroup(object):
         """``aperture``: whole map [nz, nx], host numpy array.  Returns (dict of whole-map arrays, scalars)."""
         import threading
         a = np.ascontiguousarray(aperture, dtype=np.float64)
-        assert a.shape == (self.nz, self.nx)
+        _check_shape(a.shape, (self.nz, self.nx))
         whole = {name: np.empty((self.nz, self.nx)) for name in fields}
         results = [None] * len(self._h)
 
@@ -337,8 +343,10 @@ def bulk_solve(cases, devices=(0,), fields=("pressure",), lib=None):
 
     ``cases`` is a list of ``(Params, aperture[nz, nx])`` with one common map shape (host numpy
     arrays).  Device ``d`` of ``devices`` gets the contiguous block ``dist.shard(cases, d, len(devices))``
-    -- no exchange between cases, exactly like the reference's BulkRun.  Returns a list of
-    ``(dict of arrays, dict of scalars)`` in case order."""
+    -- no exchange between cases, exactly like the reference's BulkRun.  Cases that pass the SAME array object and
+    differ only in the two boundary pressures share one unit solution inside the library (the derived ones report
+    ``iterations == 0``; ``APM_LCL_BULK_SHARE=0`` or ``params.flags = 1`` turns that off, see include/apm_lcl.h).
+    Returns a list of ``(dict of arrays, dict of scalars)`` in case order."""
     import threading
     from . import dist
     lib = lib if lib is not None else _lib.load()
@@ -350,13 +358,20 @@ def bulk_solve(cases, devices=(0,), fields=("pressure",), lib=None):
     errors = []
 
     def work(slot, device):
+        try:
+            run(slot, device)
+        except Exception as exc:           # an exception on a worker thread must reach the caller
+            errors.append((device, -1, "%s: %s" % (type(exc).__name__, exc)))
+
+    def run(slot, device):
         mine = dist.shard(index, slot, len(devices))
         if not mine:
             return
         n = len(mine)
         params = (Params * n)(*[cases[k][0] for k in mine])
         maps = [np.ascontiguousarray(cases[k][1], dtype=np.float64) for k in mine]
-        assert all(m.shape == (nz, nx) for m in maps)
+        for m in maps:
+            _check_shape(m.shape, (nz, nx))
         ptrs = (C.c_void_p * n)(*[m.ctypes.data for m in maps])
         outs = (Fields * n)()
         arrays = []

@@ -5,7 +5,10 @@ Same public surface as the reference (constructor :57-72, ``dry_run`` :74, ``sta
 ``_check_processes`` :262, ``_start_simulations`` :286).  The scheduling resource changes from CPU
 cores and host RAM to GPUs and device memory: ``num_CPUs`` bounds the number of simulations in flight,
 ``sys_RAM`` is the memory budget in GB of EACH device, and the new ``devices`` keyword lists the GPUs: a
-case goes to the device with the most free budget that can hold it (independent cases, no collective)."""
+case goes to the device with the most free budget that can hold it (independent cases, no collective).
+``spawn_delay`` / ``retest_delay`` are still accepted and honoured when given, but their defaults drop from the
+reference's 5 s (time for a child process to claim its RAM, bulk_run.py:262,286) to 0 / 0.05 s: a run is a thread
+of this process whose memory is budgeted up front, and a solve takes milliseconds."""
 import string
 from collections import defaultdict
 from itertools import product
@@ -95,7 +98,7 @@ class BulkRun(dict):
                 inp_file.RAM_req = value
 
     @staticmethod
-    def _check_processes(processes, RAM_in_use, retest_delay=5, **kwargs):
+    def _check_processes(processes, RAM_in_use, retest_delay=0.05, **kwargs):
         while True:
             for i, proc in enumerate(processes):
                 if proc.poll() is not None:
@@ -112,7 +115,7 @@ class BulkRun(dict):
             free[dev] = free.get(dev, self.avail_RAM) - ram
         return free
 
-    def _start_simulations(self, processes, RAM_in_use, spawn_delay=5, **kwargs):
+    def _start_simulations(self, processes, RAM_in_use, spawn_delay=0.0, **kwargs):
         while len(processes) < self.num_CPUs:
             free = self._free_per_device(processes, RAM_in_use)
             # emptiest device first; ties go round-robin so equal cases still spread over the GPUs
@@ -125,7 +128,8 @@ class BulkRun(dict):
                     self._next_device = order[0] + 1
                     processes.append(run_model(inp_file, device=device))
                     RAM_in_use.append(inp_file.RAM_req)
-                    sleep(spawn_delay)
+                    if spawn_delay > 0:
+                        sleep(spawn_delay)
                     break
             else:
                 break

@@ -89,6 +89,14 @@ def test_coverage_case_reproduces_golden_files(tmp_path):
     check_against_golden_files(str(tmp_path))
 
 
+def plate(tmp_path, value, nz=20, nx=16):
+    """A small parallel-plate map file (the 100 x 100 fixtures cost ~15 s per run in the CPU emulation)."""
+    path = os.path.join(str(tmp_path), "plate-%gvox.txt" % value)
+    with open(path, "w") as f:
+        f.write("\n".join(" ".join(["%.1f" % value] * nx) for _ in range(nz)) + "\n")
+    return path
+
+
 def small_inp(tmp_path, body, amap="BadApertureMap.txt"):
     return ("APER-MAP: %s\nSUMMARY-FILE: %s/log.txt\nSTAT-FILE: %s/stat.csv\nAPER-FILE: %s/aper.csv\n"
             "FLOW-FILE: %s/flow.csv\nPRESS-FILE: %s/pres.csv\nVTK-FILE: %s/data.VTK\nOVERWRITE\n"
@@ -103,7 +111,7 @@ OK_BODY = ("INLET-PRESS: 100 PA\nOUTLET-PRESS: 0 PA\nOUTLET-SIDE: TOP\nFLUID-DEN
     (OK_BODY, "BadApertureMap.txt", r"FIELD\s*\d+\s*ON THE"),
     (OK_BODY.replace("FLUID-VISCOSITY: 1.0 CP", "FLUID-VISCOSITY: -1.0 CP"), "parallel-plate-01vox.txt",
      "ERROR - NONE OR INVAILD VISCOSITY"),
-    (OK_BODY.replace("OUTLET-SIDE: TOP", "OUTLET-SIDE: NOWHERE"), "parallel-plate-01vox.txt",
+    (OK_BODY.replace("OUTLET-SIDE: TOP", "OUTLET-SIDE: NOWHERE"), "PLATE",      # detected after MAP_STATS: small map
      "INVALID OUTLET SIDE ENTERED: NOWHERE"),
     (OK_BODY + "MAXIMUM MAP DIMENSION: 50\n", "parallel-plate-01vox.txt", "MAXIMUM NUMBER OF HORIZONTAL"),
     (OK_BODY.replace("INLET-PRESS: 100 PA", "INLET-PRESS: 100"), "parallel-plate-01vox.txt", "INSUFFICIENT"),
@@ -111,6 +119,8 @@ OK_BODY = ("INLET-PRESS: 100 PA\nOUTLET-PRESS: 0 PA\nOUTLET-SIDE: TOP\nFLUID-DEN
 ])
 def test_failure_cases_return_1_with_reference_messages(tmp_path, body, amap, pattern):
     import re
+    if amap == "PLATE":
+        amap = plate(tmp_path, 1.0)
     rc, out = run(sim_lib.load(), str(tmp_path), small_inp(tmp_path, body, amap))
     assert rc == 1
     assert re.search(pattern, out), out
@@ -124,11 +134,12 @@ def test_missing_input_and_map_and_overwrite(tmp_path):
     rc, out = run(lib, str(tmp_path), "OVERWRITE\n" + OK_BODY)
     assert rc == 1 and "FATAL ERROR - NO APERTURE MAP" in out
     # second run without OVERWRITE refuses to clobber and removes nothing that existed
-    rc, out = run(lib, str(tmp_path), small_inp(tmp_path, OK_BODY, "parallel-plate-01vox.txt"))
+    amap = plate(tmp_path, 1.0)
+    rc, out = run(lib, str(tmp_path), small_inp(tmp_path, OK_BODY, amap))
     assert rc == 0, out
     assert os.path.exists(tmp_path / "data.vtk")          # extension lower-cased (IO_MODULE.F:169-170)
     assert os.path.exists(tmp_path / "flow-x.csv") and os.path.exists(tmp_path / "stat.yaml")
-    rc, out = run(lib, str(tmp_path), small_inp(tmp_path, OK_BODY, "parallel-plate-01vox.txt").replace("OVERWRITE\n", ""))
+    rc, out = run(lib, str(tmp_path), small_inp(tmp_path, OK_BODY, amap).replace("OVERWRITE\n", ""))
     assert rc == 1 and 'SPECIFY "OVERWRITE" IN THE' in out
     assert os.path.exists(tmp_path / "pres.csv")
 
@@ -139,10 +150,10 @@ def test_partially_failing_open_io_removes_what_it_created(tmp_path):
     run (after the user removed the one offender) fail on each of them in turn."""
     lib = sim_lib.load()
     (tmp_path / "pres.csv").write_text("keep me\n")
-    inp = small_inp(tmp_path, OK_BODY, "parallel-plate-01vox.txt").replace("OVERWRITE\n", "")
+    inp = small_inp(tmp_path, OK_BODY, plate(tmp_path, 1.0)).replace("OVERWRITE\n", "")
     rc, out = run(lib, str(tmp_path), inp)
     assert rc == 1 and "pres.csv ALREADY EXISTS" in out
-    left = sorted(f for f in os.listdir(tmp_path) if not f.endswith(".inp"))
+    left = sorted(f for f in os.listdir(tmp_path) if not f.endswith(".inp") and not f.startswith("plate-"))
     assert left == ["pres.csv"], left
     assert (tmp_path / "pres.csv").read_text() == "keep me\n"
     os.remove(tmp_path / "pres.csv")
@@ -154,7 +165,8 @@ def test_units_and_rate_bc_through_files(tmp_path):
     body = ("INLET-RATE: 1.0 MM^3/SEC\nOUTLET-PRESS: 1 KPA\nOUTLET-SIDE: RIGHT\nFLUID-DENSITY: 1 G/CM^3\n"
             "FLUID-VISCOSITY: 1.0 CP\nMAP AVERAGING FACTOR: 10\nVOXEL SIZE: 10 MICRONS\nLOW-MASK: 0.0001\n"
             "OUTPUT-UNITS: KPA,MM,MM^3/SEC\n")
-    rc, out = run(sim_lib.load(), str(tmp_path), small_inp(tmp_path, body, "parallel-plate-10vox.txt"))
+    nz, nx = 20, 16
+    rc, out = run(sim_lib.load(), str(tmp_path), small_inp(tmp_path, body, plate(tmp_path, 10.0, nz, nx)))
     assert rc == 0, out
     assert "FRACTURE FLOW IS RATE CONTROLLED" in out
     import yaml
@@ -164,7 +176,7 @@ def test_units_and_rate_bc_through_files(tmp_path):
     assert st["INLET PRESS"][0] > 1.0
     assert st["DENSITY"] == [1.0, "G/CM^3"]
     # analytic cubic law for a 10-voxel parallel plate gives the inlet pressure
-    w = l = 100 * 10e-6 * 10
+    w, l = nz * 10e-6 * 10, nx * 10e-6 * 10        # outlet RIGHT: the flow runs along x
     b = 10 * 10e-6
     dp = 1e-9 * 12 * 1e-3 * l / (w * b ** 3)
     assert (st["INLET PRESS"][0] - 1.0) * 1e3 == pytest.approx(dp, rel=1e-6)

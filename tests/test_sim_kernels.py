@@ -94,7 +94,7 @@ def test_sim_synthetic_contact_map(sim):
     assert so["zeros"] > 0
 
 
-@pytest.mark.parametrize("base", [1e5, 1e7, 1e9])
+@pytest.mark.parametrize("base", [1e7, 1e9])      # 1e5 as well in the GPU variant (tests/test_gpu_parity.py)
 def test_sim_back_pressure_does_not_cost_flux_accuracy(sim, base):
     """A common pressure offset must not change the fluxes (they are pressure differences): the solve runs on
     the unit drop and is shifted afterwards.  Solving for absolute pressures lost 1e-3 of the local fluxes at

@@ -56,7 +56,9 @@ def check_against_oracle(p, a, ptol=1e-6, qtol=1e-6, pmask=None):
     qscale = np.abs(o["flow_m"]).max()
     for k in ("flow_x", "flow_z", "flow_m"):
         assert np.abs(f[k] - o[k]).max() <= 1e-5 * qscale
-    assert np.abs(f["reynolds"] - o["reynolds"]).max() <= 1e-5 * np.abs(o["reynolds"]).max()
+    # REN = rho/mu QM / WIDTH: weighted by WIDTH this is the flux bar again (in a contact cell, WIDTH = the LOW-MASK
+    # clamp, the division blows the flux noise of the solve up by 1e4 against the open cells that set max REN)
+    assert np.abs((f["reynolds"] - o["reynolds"]) * o["width"]).max() <= 1e-5 * np.abs(o["reynolds"] * o["width"]).max()
     assert np.array_equal(f["aperture"], o["width"])
     r = f["residual"]
     if not np.isnan(r).all():          # every Q5 == 0 gives 0/0 = NaN, exactly like the reference (:826)

@@ -25,9 +25,11 @@ for share, stream_counts in (("0", (1, 2, 4, 8)), ("1", (1, 4))):
     os.environ["APM_LCL_BULK_SHARE"] = share
     for streams in stream_counts:
         os.environ["APM_LCL_BULK_STREAMS"] = str(streams)
-        t0 = time.time()
-        res = lcl.bulk_solve(cases, devices=(0,), fields=("pressure",))
-        dt = time.time() - t0
+        dt = 1e30
+        for _ in range(3):             # best of three: the wall clock of this host-fed loop is noisy on a shared box
+            t0 = time.time()
+            res = lcl.bulk_solve(cases, devices=(0,), fields=("pressure",))
+            dt = min(dt, time.time() - t0)
         ok = all(s["converged"] == 1 for _, s in res)
         solved = sum(s["iterations"] > 0 for _, s in res)
         print("n=%d cases=%d (PCG solves: %d) share=%s streams=%d wall=%.3f s  %.2f ms/case  %.1f Mcells/s  all converged=%s" %

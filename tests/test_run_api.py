@@ -136,3 +136,52 @@ def test_input_file_matches_reference_implementation():
     ref.update(upd)
     assert str(ours) == str(ref)
     assert ours.filename_format_args == ref.filename_format_args
+
+
+def test_bulk_run_schedules_by_per_device_memory(monkeypatch):
+    """``sys_RAM`` is the budget of EACH device, a case goes to the device with the most room, and
+    never more than ``num_CPUs`` simulations are in flight (scheduling only: ``run_model`` is replaced by a stub)."""
+    from apmapflow_b200.run_model import bulk_run as br
+
+    class Handle:
+        def __init__(self, inp, device):
+            self.input_file, self.device, self.polls = inp, device, 0
+
+        def poll(self):
+            self.polls += 1
+            return 0 if self.polls > 2 else None
+
+    started, peak = [], {}
+    in_flight = []
+
+    def fake_run_model(inp, device=0, **kw):
+        h = Handle(inp, device)
+        started.append((inp.tag, device))
+        in_flight[:] = [p for p in in_flight if p.polls <= 2] + [h]
+        used = {}
+        for p in in_flight:
+            used[p.device] = used.get(p.device, 0.0) + p.input_file.RAM_req
+        for d, u in used.items():
+            peak[d] = max(peak.get(d, 0.0), u)
+        peak["n"] = max(peak.get("n", 0), len(in_flight))
+        return h
+
+    monkeypatch.setattr(br, "run_model", fake_run_model)
+    sizes = {"big": 6.0, "mid": 3.0, "small": 1.0}
+    monkeypatch.setattr(br, "estimate_req_RAM", lambda maps, avail, **kw: [sizes[os.path.basename(m)] for m in maps])
+    inp = InputFile(os.path.join(GOLDEN, "test-model-inputs.txt"))
+    bulk = BulkRun(inp, num_CPUs=3, sys_RAM=8.0, devices=[0, 1], spawn_delay=0.0, retest_delay=0.0)
+    for k, name in enumerate(["big", "big", "mid", "mid", "small", "small", "small", "big"]):
+        case = inp.clone()
+        case["APER-MAP"] = name
+        case.tag = "%s-%d" % (name, k)
+        bulk.input_file_list.append(case)
+    bulk.start()
+    assert sorted(t for t, _ in started) == sorted("%s-%d" % (n, k) for k, n in
+                                                   enumerate(["big", "big", "mid", "mid", "small", "small", "small", "big"]))
+    assert {d for _, d in started} == {0, 1}                      # both devices used
+    assert peak[0] <= bulk.avail_RAM and peak[1] <= bulk.avail_RAM  # 7.2 GB each: two "big" never share a device
+    assert peak["n"] <= 3
+    assert started[0][1] != started[1][1]                          # equal first cases go to different devices
+    with pytest.raises(EnvironmentError):                          # a map no device can hold is refused up front
+        rm.estimate_req_RAM([os.path.join(GOLDEN, "parallel-plate-01vox.txt")], 1e-9)

@@ -404,7 +404,8 @@ def main():
     if rank != 0:
         return finish()
     traffic = None
-    tpath = os.path.join(ROOT, "profiles", "r02_ncu_traffic.json")     # ncu capture of these kernels (tools/r02_measure.sh)
+    # ncu capture of these kernels, final code of round 2 (tools/r02_final_profile.sh + tools/ncu_raw_to_json.py)
+    tpath = os.path.join(ROOT, "profiles", "r02_ncu_traffic_final.json")
     if os.path.exists(tpath) and world == 1:
         tj = json.load(open(tpath))
         if tj.get("size") == n and dom in tj["kernels"]:

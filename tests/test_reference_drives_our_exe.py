@@ -89,8 +89,8 @@ def test_reference_bulk_run_drives_our_executable(ref, sim_exe, tmp_path):
     want = [os.path.join(str(tmp_path), "bulk", "%sPA-STAT-FILE.yaml" % p) for p in ("100", "200", "300")]
     logs = [w.replace("STAT-FILE.yaml", "SUMMARY-FILE") for w in want]
 
-    def finished(path):                # the transcript's last line is written when every output file is closed
-        return os.path.isfile(path) and "EXITING PROGRAM" in open(path).read()
+    def finished(path):                # the log file ends with this line (tests/golden/coverage_test_log-orig.txt), written once every output file is closed
+        return os.path.isfile(path) and "OUTPUT FILES CLOSED" in open(path).read()
     while time.time() < deadline and not all(finished(p) for p in logs):
         time.sleep(0.2)
     rates = []

@@ -37,14 +37,30 @@ struct dim3 {
     dim3(int a) : x((unsigned)a) {}
 };
 
+// Fiber switch.  glibc's swapcontext saves and restores the signal mask with a system call on every switch; a kernel
+// with a few barriers per thread spends nearly all of its emulated time there.  On x86-64 the switch is twenty lines of
+// assembly instead (sim_globals.cpp: callee-saved registers and the stack pointer, nothing else changes between fibers).
+#if defined(__x86_64__)
+#define CUSIM_FAST_SWITCH 1
+extern "C" void cusim_switch(void **save_sp, void *load_sp);
+#endif
+
 namespace cusim {
 struct Fiber {
+#ifdef CUSIM_FAST_SWITCH
+    void *sp = nullptr;
+#else
     ucontext_t ctx;
+#endif
     char *stack = nullptr;
     bool done = true;
 };
 inline std::vector<Fiber> &fibers() { static std::vector<Fiber> f; return f; }
+#ifdef CUSIM_FAST_SWITCH
+inline void *&sched() { static void *sp = nullptr; return sp; }
+#else
 inline ucontext_t &sched() { static ucontext_t c; return c; }
+#endif
 inline int &cur() { static int c = 0; return c; }
 inline int &nthreads() { static int n = 0; return n; }
 inline int &bar_count() { static int n = 0; return n; }
@@ -59,6 +75,28 @@ struct WarpX {
 inline std::vector<WarpX> &warps() { static std::vector<WarpX> w; return w; }
 constexpr size_t kStack = 256 * 1024;
 
+#ifdef CUSIM_FAST_SWITCH
+inline void yield() { cusim_switch(&fibers()[cur()].sp, sched()); }
+inline void entry()
+{
+    (*body())();
+    fibers()[cur()].done = true;
+    cusim_switch(&fibers()[cur()].sp, sched());
+    __builtin_trap();   // a finished fiber is never resumed
+}
+// a fresh fiber: six zeroed callee-saved registers, then the address `ret` jumps to, then a slot that keeps the stack
+// 16-byte aligned at the entry of entry() the way a call would
+inline void prepare(Fiber &f)
+{
+    void **top = (void **)(((uintptr_t)f.stack + kStack) & ~(uintptr_t)15);
+    *--top = nullptr;
+    *--top = (void *)entry;
+    for (int k = 0; k < 6; k++) *--top = nullptr;
+    f.sp = (void *)top;
+    f.done = false;
+}
+inline void resume(Fiber &f) { cusim_switch(&sched(), f.sp); }
+#else
 inline void yield() { swapcontext(&fibers()[cur()].ctx, &sched()); }
 inline void entry()
 {
@@ -66,6 +104,17 @@ inline void entry()
     fibers()[cur()].done = true;
     swapcontext(&fibers()[cur()].ctx, &sched());
 }
+inline void prepare(Fiber &f)
+{
+    getcontext(&f.ctx);
+    f.ctx.uc_stack.ss_sp = f.stack;
+    f.ctx.uc_stack.ss_size = kStack;
+    f.ctx.uc_link = nullptr;
+    makecontext(&f.ctx, (void (*)())entry, 0);
+    f.done = false;
+}
+inline void resume(Fiber &f) { swapcontext(&sched(), &f.ctx); }
+#endif
 }   // namespace cusim
 
 extern dim3 threadIdx, blockIdx, blockDim, gridDim;
@@ -190,14 +239,7 @@ inline void launch(dim3 grid, dim3 block, size_t smem, std::function<void()> fn)
     for (unsigned b = 0; b < grid.x; b++) {
         bar_count() = 0;
         for (auto &w : warps()) w.count = 0;
-        for (int i = 0; i < nt; i++) {
-            getcontext(&fb[i].ctx);
-            fb[i].ctx.uc_stack.ss_sp = fb[i].stack;
-            fb[i].ctx.uc_stack.ss_size = kStack;
-            fb[i].ctx.uc_link = nullptr;
-            makecontext(&fb[i].ctx, (void (*)())entry, 0);
-            fb[i].done = false;
-        }
+        for (int i = 0; i < nt; i++) prepare(fb[i]);
         int remaining = nt;
         while (remaining > 0) {
             for (int i = 0; i < nt; i++) {
@@ -205,7 +247,7 @@ inline void launch(dim3 grid, dim3 block, size_t smem, std::function<void()> fn)
                 cur() = i;
                 threadIdx = dim3(i);
                 blockIdx = dim3(b);
-                swapcontext(&sched(), &fb[i].ctx);
+                resume(fb[i]);
                 if (fb[i].done) remaining--;
             }
         }

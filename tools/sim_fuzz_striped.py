@@ -1,7 +1,8 @@
 """Randomised check of the STRIPED solve on the CPU emulation (tests/sim; test infrastructure): random map shapes, 2-4
 gloo ranks, outlet sides, boundary-condition modes, W-levels and striping thresholds, each compared with the single-rank
 solve of the same map through the assertions of tests/test_striped_sim.py::compare.  One line per failure with the
-parameters that reproduce it.
+parameters that reproduce it.  Blocked fractures (no open path from inlet to outlet) are skipped for the reason given in
+tools/gpu_fuzz_parity.py: two iterative solves to 1e-10 agree on nothing but noise at the scale of the LOW-MASK leak.
 
     python tools/sim_fuzz_striped.py [--seconds 300] [--seed 0]
 """
@@ -14,11 +15,13 @@ import traceback
 from pathlib import Path
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-for p in (ROOT, os.path.join(ROOT, "netl-ap-map-flow_b200"), os.path.join(ROOT, "tests")):
+for p in (ROOT, os.path.join(ROOT, "netl-ap-map-flow_b200"), os.path.join(ROOT, "tests"), os.path.join(ROOT, "tools")):
     sys.path.insert(0, p)
-os.environ["PYTHONPATH"] = os.pathsep.join(sys.path[:3] + [os.environ.get("PYTHONPATH", "")])   # spawned ranks
+os.environ["PYTHONPATH"] = os.pathsep.join(sys.path[:4] + [os.environ.get("PYTHONPATH", "")])   # spawned ranks
 import numpy as np  # noqa: E402
 from apmapflow_b200._lib import LEFT, RIGHT, TOP, BOTTOM  # noqa: E402
+from gpu_fuzz_parity import has_open_path  # noqa: E402
+from helpers import synth_aperture  # noqa: E402
 
 
 def main():
@@ -47,6 +50,9 @@ def main():
         env_w = {}
         if rng.random() < 0.3:
             env_w = {"APM_LCL_W_LO": "1", "APM_LCL_W_HI": "2"}
+        a = synth_aperture(nz, nx, seed=seed, sigma_c=4, contact=0.15, sigma_k=6)     # the map test_striped_sim's ranks build
+        if not has_open_path(a, 1e-4, side in (TOP, BOTTOM)):
+            continue
         case = dict(world=world, shape=(nz, nx), seed=seed, mode=mode, side=side, min_cells=min_cells, w=env_w)
         old = {k: os.environ.get(k) for k in env_w}
         os.environ.update(env_w)

@@ -6,7 +6,7 @@
 //                                                                          in registers, never stored)
 //   COEF                       apmapflow/src/APM_MODULE.F:142-271         (tapered-plate half cells)
 //   FLOW_BOUNDARY              apmapflow/src/APM_MODULE.F:277-376         (2x / 0 boundary faces)
-// Roofline: 8 B read + 24 B written per cell, but 4 atan and a dozen divisions in FP64 per cell make it
+// Roofline: 8 B read + 24 B written per cell, but 4 atan and half a dozen divisions in FP64 per cell make it
 // FP64-pipe bound, not HBM bound.  It runs once per solve.
 #include "device_utils.cuh"
 
@@ -14,6 +14,11 @@ namespace lcl {
 
 struct CondParams {
     double high, low, rough, vox, visc, dx, dz;
+    // loop constants of the interior faces, so that a face costs three divisions instead of seven: 1 / (d/2) for the
+    // taper angle, and (DZ/12) / AVG_VISC / (DX/2) resp. (DX/12) / AVG_VISC / (DZ/2) for the two half cells in series
+    // (APM_MODULE.F:213,235,266-267).  The products differ from the reference's chain of divisions in the last ulp or
+    // two, like the merged division in tapered_b3; the parity bar on conductances is 1e-9.
+    double inv_hx, inv_hz, kx, kz;
     int side;
 };
 
@@ -30,9 +35,9 @@ __device__ __forceinline__ double clampa(double a, double high, double low)
 // the last ulp or two of the two libm calls -- the same uncertainty any other libm has, and what the
 // 1e-9 parity bar on conductances already allows for -- so the tangent (half of this kernel's FP64
 // work) is not recomputed.
-__device__ __forceinline__ double tapered_b3(double a, double b, double dhalf)
+__device__ __forceinline__ double tapered_b3(double a, double b, double inv_dhalf)
 {
-    const double t = fabs(a - b) / dhalf;
+    const double t = fabs(a - b) * inv_dhalf;
     const double theta = atan(t);
     const double x = t - theta;
     const double num = (2.0 * (a * a)) * (b * b);
@@ -42,8 +47,9 @@ __device__ __forceinline__ double tapered_b3(double a, double b, double dhalf)
     return ((num * 3.0) * x) / ((a + b) * ((t * t) * t));
 }
 
-// two half-cell terms in series across a face: 1 / (d/B1 + d/B2) = B1 B2 / (d (B1 + B2)), one division
-__device__ __forceinline__ double series(double b1, double b2, double d) { return (b1 * b2) / (d * (b1 + b2)); }
+// two half-cell terms in series across a face, times the face's constant k = (width/12) / visc / d:
+// k / (d/B1 + d/B2) d = k B1 B2 / (B1 + B2), one division
+__device__ __forceinline__ double series(double b1, double b2, double k) { return ((b1 * b2) * k) / (b1 + b2); }
 
 struct ApView {
     const double *a;
@@ -112,12 +118,11 @@ k_conductance(const double *__restrict__ ap, int nz, int nx, int zlo, int zhi, C
         // right face
         double fx;
         {
-            const double dbp = p.dx / 2;
-            const double bp3 = tapered_b3(w, rht, dbp);
+            const double bp3 = tapered_b3(w, rht, p.inv_hx);
             if (x < nx - 1) {
                 const double wn = width_of(A.at(z, x + 1), p);
-                const double bf3 = tapered_b3(rht, wn, dbp);
-                fx = series(bp3, bf3, dbp) * (p.dz / 12) / p.visc;           // :213,266
+                const double bf3 = tapered_b3(rht, wn, p.inv_hx);
+                fx = series(bp3, bf3, p.kx);                                   // :213,266
                 if (x == 0) txl[z] = lr_outlet ? 2 * fx : 0.0;                 // :309,324 / :339,354
             } else {
                 fx = (p.dz * bp3) / (12.0 * p.dx) / p.visc;                    // :249
@@ -129,12 +134,11 @@ k_conductance(const double *__restrict__ ap, int nz, int nx, int zlo, int zhi, C
         // top face
         double fz;
         {
-            const double dbp = p.dz / 2;
-            const double bp3 = tapered_b3(w, top, dbp);
+            const double bp3 = tapered_b3(w, top, p.inv_hz);
             if (z < nz - 1) {
                 const double wn = width_of(A.at(z + 1, x), p);
-                const double bf3 = tapered_b3(top, wn, dbp);
-                fz = series(bp3, bf3, dbp) * (p.dx / 12) / p.visc;           // :235
+                const double bf3 = tapered_b3(top, wn, p.inv_hz);
+                fz = series(bp3, bf3, p.kz);                                   // :235,267
                 if (z == 0) tzb[x] = lr_outlet ? 0.0 : 2 * fz;                 // :311 / :341
             } else {
                 fz = (p.dz * bp3) / (12.0 * p.dx) / p.visc;                    // :262 (sic DZ/DX)
@@ -194,6 +198,8 @@ void launch_conductance(Solver &s, const apm_lcl_params &p, const double *ap_dev
     // DIAM = NX*VOX*AVG, DX = DIAM/NX (APERTURE_MAP_FLOW.F:462-463, APM_MODULE.F:173-174)
     const double diam = s.nx * p.voxel_size * p.avg_factor, leng = s.nz * p.voxel_size * p.avg_factor;
     c.dx = diam / s.nx; c.dz = leng / s.nz;
+    c.inv_hx = 1.0 / (c.dx / 2); c.inv_hz = 1.0 / (c.dz / 2);
+    c.kx = (c.dz / 12) / c.visc / (c.dx / 2); c.kz = (c.dx / 12) / c.visc / (c.dz / 2);
     c.side = p.outlet_side;
     const int grid = grid_for(s, s.zhi - s.zlo, s.nx, 8);
     LAUNCH(k_conductance, grid, kBlock, 0, s.stream, ap_dev, s.nz, s.nx, s.zlo, s.zhi, c, s.width, s.tx, s.tz, s.txl, s.tzb,

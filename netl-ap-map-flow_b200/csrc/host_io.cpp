@@ -13,6 +13,7 @@
 #include <algorithm>
 #include <cctype>
 #include <cerrno>
+#include <charconv>
 #include <chrono>
 #include <cmath>
 #include <condition_variable>
@@ -645,6 +646,21 @@ int parse_map_line(const char *p, const char *end, int maxfld, std::vector<doubl
     const char *fs = nullptr;
     int nfld = 0;
     auto close = [&](const char *fe) {
+        // plain decimal fields ("12.5", "1e0", "-3.E-2", "+.5") go through std::from_chars -- correctly rounded like
+        // strtod, a sixth of its cost, and a whole map is 1e7..1e8 of them; anything else (D exponents, stray letters,
+        // out-of-range values, signs in odd places) takes the Fortran-minded path below
+        {
+            const char *q = fs;
+            bool plain = fe > fs;
+            for (const char *c = fs; c < fe && plain; c++)
+                plain = (*c >= '0' && *c <= '9') || *c == '.' || *c == '-' || *c == '+' || *c == 'e' || *c == 'E';
+            if (plain && *q == '+') q++;
+            if (plain && q < fe && *q != '+') {
+                double v;
+                const auto res = std::from_chars(q, fe, v);
+                if (res.ec == std::errc() && res.ptr == fe) { vals.push_back(v); return; }
+            }
+        }
         char tmp[128];
         size_t len = (size_t)(fe - fs);
         if (len >= sizeof tmp) len = sizeof tmp - 1;
@@ -687,7 +703,19 @@ bool read_data_map(Run &r)
         r.to_stdout("IO ERROR: " + std::to_string(errno) + " ATTEMPTING TO OPEN: " + r.apm_file);
         return false;
     }
-    std::string text((std::istreambuf_iterator<char>(in)), std::istreambuf_iterator<char>());
+    std::string text;
+    in.seekg(0, std::ios::end);
+    const std::streamoff size = in.tellg();
+    if (size > 0) {             // one read of the whole file (the iterator pair copies byte by byte: 0.3 GB/s)
+        text.resize((size_t)size);
+        in.seekg(0, std::ios::beg);
+        in.read(&text[0], size);
+        text.resize((size_t)in.gcount());
+    } else {                    // not seekable: whatever the stream gives
+        in.clear();
+        in.seekg(0, std::ios::beg);
+        text.assign((std::istreambuf_iterator<char>(in)), std::istreambuf_iterator<char>());
+    }
     in.close();
     std::vector<std::vector<double>> rows;
     int nx = 0;

@@ -180,3 +180,44 @@ def test_units_and_rate_bc_through_files(tmp_path):
     b = 10 * 10e-6
     dp = 1e-9 * 12 * 1e-3 * l / (w * b ** 3)
     assert (st["INLET PRESS"][0] - 1.0) * 1e3 == pytest.approx(dp, rel=1e-6)
+
+
+def test_map_reader_notations_and_separators(tmp_path):
+    """READ_DATA_MAP through LNPROC accepts blanks, commas, TABs and '=' as separators and every Fortran spelling of a
+    real (MAP_MODULE.F:18-85, STRING_MODULE.F:114-239).  The reader's fast path (std::from_chars on plain decimal
+    fields) and its Fortran-minded path (D exponents, leading '+', ...) must agree: the same values written in different
+    notations give byte-identical output files; a field that is no number fails with the reference's message."""
+    lib = sim_lib.load()
+    rows = [[1.0, 2.5, 0.5, 3.0, 12.0, 7.25], [4.0, 1.5, 2.0, 0.25, 9.0, 1.0], [2.0, 2.0, 6.5, 1.0, 3.0, 8.0],
+            [5.0, 0.75, 1.0, 2.0, 4.0, 4.0]]
+    plain = "\n".join(" ".join("%.6f" % v for v in row) for row in rows) + "\n"
+    spell = {1.0: ["1", "1.", "1e0", "1E0", "+1.0", "1d0", "1.0D+00", "0.1e1", "10.E-1"], 2.5: ["2.5", "+2.5", ".25e1", "2.5D0", "25e-1"],
+             0.5: [".5", "0.5", "5.E-1", "+.5", "5d-1"], 0.25: [".25", "2.5e-1"], 0.75: ["0.75", "7.5D-1"]}
+    out = []
+    for z, row in enumerate(rows):
+        toks = []
+        for x, v in enumerate(row):
+            forms = spell.get(v, ["%g" % v, "%.3f" % v, "%.3E" % v])
+            toks.append(forms[(z * 7 + x) % len(forms)])
+        sep = [" ", ",", "\t", "  ,  ", " = "][z % 5]
+        out.append(sep.join(toks) + ("   ; a comment" if z == 1 else ""))
+    mixed = "\r\n".join(out) + "\r\n\n"
+    results = []
+    for name, text in (("plain", plain), ("mixed", mixed)):
+        work = tmp_path / name
+        work.mkdir()
+        (work / "map.txt").write_text(text)
+        rc, log = run(lib, str(work), small_inp(work, OK_BODY, str(work / "map.txt")))
+        assert rc == 0, log
+        results.append({f: (work / f).read_text() for f in ("aper.csv", "pres.csv", "flow-z.csv", "flow-x.csv")})
+    assert results[0] == results[1]
+    bad = tmp_path / "bad"
+    bad.mkdir()
+    (bad / "map.txt").write_text("1.0 2.0 3.0\n1.0 2..0 3.0\n")
+    rc, log = run(lib, str(bad), small_inp(bad, OK_BODY, str(bad / "map.txt")))
+    import re
+    assert rc == 1 and re.search(r"FIELD\s*2\s*ON THE", log), log
+    for token in ("1e", "0x10", "nan", "--1", "1e+"):
+        (bad / "map.txt").write_text("1.0 2.0 3.0\n1.0 %s 3.0\n" % token)
+        rc, log = run(lib, str(bad), small_inp(bad, OK_BODY, str(bad / "map.txt")))
+        assert rc == 1 and re.search(r"FIELD\s*2\s*ON THE", log), (token, log)

@@ -1160,18 +1160,21 @@ int run(Run &r, const std::vector<int> &devices)
         for (int ix = 0; ix < nx; ix++) xs[ix + 1] = xs[ix] + dx;
         zs[0] = 0.0;
         for (int iz = 0; iz < nz; iz++) zs[iz + 1] = zs[iz] + dz;
+        // the x coordinate of a column and the z coordinate of a row are the same text in every record that shows them:
+        // formatted once (two thirds of the conversions of this section)
+        std::string xtext;
+        for (int ix = 0; ix <= nx; ix++) { append_E(xtext, 14, 6, xs[(size_t)ix]); xtext += ' '; }
         for (int sgn = -1; sgn <= 1; sgn += 2) {
             write_rows_parallel(f, (long long)nz + 1, [&, sgn](long long iz, std::string &buf) {
                 // rows 0..nz-1 use the bottom corners of row iz, the last record the top corners of row nz-1
                 const int cz = iz < nz ? (int)iz - 1 : nz - 1;
-                const double Z = zs[(size_t)iz];
+                std::string ztext(1, ' ');
+                append_E(ztext, 14, 6, zs[(size_t)iz]);
+                ztext += '\n';
                 for (int ix = -1; ix < nx; ix++) {
-                    append_E(buf, 14, 6, xs[(size_t)(ix + 1)]);
-                    buf += ' ';
+                    buf.append(xtext, (size_t)(ix + 1) * 15, 15);
                     append_E(buf, 14, 6, sgn * (corner(clamped, nx, nz, cz, ix) * pm) / 2.0);
-                    buf += ' ';
-                    append_E(buf, 14, 6, Z);
-                    buf += '\n';
+                    buf += ztext;
                 }
             });
         }

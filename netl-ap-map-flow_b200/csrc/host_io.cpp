@@ -78,6 +78,10 @@ std::string fixed(const std::string &s, size_t n)
 // the files are byte-identical to the sequential writer.
 unsigned io_threads()
 {
+    if (const char *e = getenv("APM_LCL_IO_THREADS")) {   // 1 = the sequential writers and reader
+        const int k = atoi(e);
+        if (k >= 1) return k > 256 ? 256u : (unsigned)k;
+    }
     unsigned n = std::thread::hardware_concurrency();
     if (n == 0) n = 4;
     return n > 32 ? 32 : n;

@@ -221,3 +221,19 @@ def test_map_reader_notations_and_separators(tmp_path):
         (bad / "map.txt").write_text("1.0 2.0 3.0\n1.0 %s 3.0\n" % token)
         rc, log = run(lib, str(bad), small_inp(bad, OK_BODY, str(bad / "map.txt")))
         assert rc == 1 and re.search(r"FIELD\s*2\s*ON THE", log), (token, log)
+
+
+def test_parallel_writers_and_reader_equal_the_sequential_ones(tmp_path, monkeypatch):
+    """APM_LCL_IO_THREADS=1 takes the sequential reader and writers; any other count must give the same bytes in every
+    output file (rows are formatted by a pool of threads and written in order)."""
+    lib = sim_lib.load()
+    outs = {}
+    for threads in ("1", "3", "16"):
+        monkeypatch.setenv("APM_LCL_IO_THREADS", threads)
+        work = tmp_path / ("t" + threads)
+        work.mkdir()
+        rc, log = run(lib, str(work), coverage_inp(), "coverage_test.inp")
+        assert rc == 0, log
+        outs[threads] = {f: (work / f).read_bytes() for f in sorted(os.listdir(work)) if f != "coverage_test_log.txt"}
+        assert len(outs[threads]) >= 9
+    assert outs["1"] == outs["3"] == outs["16"]

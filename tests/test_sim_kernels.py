@@ -165,3 +165,32 @@ def test_sim_preconditioner_is_symmetric_positive(sim, monkeypatch, w_levels):
     aa, bb, ab, ba = ma @ va, mb @ vb, ma @ vb, mb @ va
     assert aa > 0 and bb > 0
     assert abs(ab - ba) <= 1e-10 * np.sqrt(aa * bb)
+
+
+def test_sim_bulk_solve_reports_failed_cases_and_keeps_the_others(sim):
+    """apm_lcl_bulk_solve returns the number of failed cases, marks them converged = 0, keeps the first message and still
+    delivers every other case (include/apm_lcl.h); a case that runs out of iterations inside a group of shared unit
+    solutions must not poison the cases after it."""
+    import ctypes as C
+    from apmapflow_b200._lib import Fields, Scalars
+    a = synth_aperture(24, 20, seed=5, sigma_c=3, contact=0.1, sigma_k=5)
+    kw = dict(voxel_size=1e-5, avg_factor=1.0, viscosity=1e-3)
+    cases = [params(**kw), params(**dict(kw, viscosity=-1.0)), params(inlet_rate=1e-9, **kw),          # ok, bad, bad
+             params(outlet_pressure=250.0, **kw), params(max_iter=1, **kw), params(outlet_pressure=500.0, **kw)]
+    n = len(cases)
+    arr = (Params * n)(*cases)
+    maps = (C.c_void_p * n)(*[a.ctypes.data] * n)
+    outs = (Fields * n)()
+    pres = [np.full(a.shape, np.nan) for _ in range(n)]
+    for k in range(n):
+        outs[k].pressure = pres[k].ctypes.data
+    scal = (Scalars * n)()
+    failed = sim.apm_lcl_bulk_solve(0, a.shape[1], a.shape[0], n, arr, maps, outs, scal)
+    assert failed == 3
+    assert [scal[k].converged for k in range(n)] == [1, 0, 0, 1, 0, 1]
+    assert b"VISCOSITY" in sim.apm_lcl_last_error()          # the message of the first failed case
+    for k, p_out in ((0, 0.0), (3, 250.0), (5, 500.0)):
+        f, s = lcl.lcl_solve(cases[k], a, fields=("pressure",), lib=sim)
+        assert np.abs(pres[k] - f["pressure"]).max() <= 1e-9 * 100.0
+        assert scal[k].flow == pytest.approx(s["flow"], rel=1e-8) and scal[k].outlet_pressure == p_out
+    assert scal[3].iterations == 0 and scal[5].iterations == 0      # derived from case 0's unit solution

@@ -185,3 +185,34 @@ def test_bulk_run_schedules_by_per_device_memory(monkeypatch):
     assert started[0][1] != started[1][1]                          # equal first cases go to different devices
     with pytest.raises(EnvironmentError):                          # a map no device can hold is refused up front
         rm.estimate_req_RAM([os.path.join(GOLDEN, "parallel-plate-01vox.txt")], 1e-9)
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/apmapflow"), reason="reference tree not present (GPU box)")
+def test_bulk_run_input_files_match_reference_implementation():
+    """Live diff against the reference's own BulkRun in the authoring container: the same YAML description must give
+    the same list of input files -- order, file names and every line of their text (bulk_run.py:130-234)."""
+    import yaml
+    sys.path.insert(0, "/root/reference")
+    try:
+        from apmapflow.run_model import BulkRun as RefBulkRun, InputFile as RefInputFile
+    except Exception as exc:
+        pytest.skip("reference package not importable: %s" % exc)
+    finally:
+        sys.path.remove("/root/reference")
+    cfg = yaml.safe_load(open(os.path.join(GOLDEN, "test-bulk-run.yaml")))
+    path = os.path.join(GOLDEN, cfg["initial_input_file"])
+    lists = []
+    for bulk_cls, inp_cls in ((BulkRun, InputFile), (RefBulkRun, RefInputFile)):
+        inp = inp_cls(path)
+        for key in ("APER-MAP", "SUMMARY-FILE", "STAT-FILE", "APER-FILE", "FLOW-FILE", "PRESS-FILE", "VTK-FILE"):
+            inp[key].commented_out = False
+        bulk = bulk_cls(inp, **cfg["bulk_run_keyword_args"])
+        bulk.generate_input_files(cfg["default_run_parameters"], cfg["default_file_formats"],
+                                  case_identifer=cfg["case_identifier"], case_params=cfg["case_parameters"])
+        lists.append([(f.outfile_name, str(f)) for f in bulk.input_file_list])
+        # a second description appended to the first (what apm_bulk_run does with several YAML files)
+        bulk.generate_input_files({"OUTLET-PRESS": ["50"], "aper-map": ["parallel-plate-01vox"], "ROUGHNESS": ["0.00"]},
+                                  cfg["default_file_formats"], append=True)
+        lists.append([(f.outfile_name, str(f)) for f in bulk.input_file_list])
+    assert lists[0] == lists[2] and len(lists[0]) == 16
+    assert lists[1] == lists[3] and len(lists[1]) == 17

@@ -216,3 +216,59 @@ def test_bulk_run_input_files_match_reference_implementation():
         lists.append([(f.outfile_name, str(f)) for f in bulk.input_file_list])
     assert lists[0] == lists[2] and len(lists[0]) == 16
     assert lists[1] == lists[3] and len(lists[1]) == 17
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/apmapflow"), reason="reference tree not present (GPU box)")
+def test_arg_input_differential_against_reference():
+    """20 000 random input-file lines -- keywords with and without colons, values, units, quotes, comments, leading
+    semicolons, odd spacing -- through both ArgInput implementations: same keyword, value, unit, comment, flag and the
+    same line written back, also after changing the value and the unit."""
+    import random
+    sys.path.insert(0, "/root/reference")
+    try:
+        from apmapflow.run_model.run_model import ArgInput as RefArgInput
+    except Exception as exc:
+        pytest.skip("reference package not importable: %s" % exc)
+    finally:
+        sys.path.remove("/root/reference")
+    rng = random.Random(20240601)
+    keys = ["INLET-PRESS:", "OUTLET-SIDE:", "APER-MAP:", "MAP AVERAGING FACTOR:", "VOXEL SIZE:", "OVERWRITE", "EXE-FILE:",
+            "ROUGHNESS REDUCTION:", "KEY", "K:", ":", "A:B:", "HIGH-MASK:", "OUTPUT-UNITS:", ""]
+    vals = ["100", "1.0E-3", "TOP", '"a b.txt"', '"unterminated', "C:\\\\maps\\\\m.txt", "./rel/path.txt", "PA,MM,MM^3/MIN",
+            "a=b", "10 MICRONS", "", "x y z", "'single'", "-5", "1e0", "\ttab"]
+    units = ["PA", "KPA", "MICRONS", "CP", "", "KG/M^3", "unit with blanks"]
+    comments = ["", ";comment", " ; spaced comment", ";;double", ";c1 ;c2", " ;"]
+
+    def same(a, b, what, line):
+        for attr in ("keyword", "value", "unit", "comment_msg", "commented_out", "line"):
+            assert getattr(a, attr) == getattr(b, attr), (what, attr, line, getattr(a, attr), getattr(b, attr))
+
+    compared = 0
+    for _ in range(20000):
+        parts = [rng.choice(["", ";", "; ", ";;"]) if rng.random() < 0.3 else "", rng.choice(keys)]
+        if rng.random() < 0.85:
+            parts.append(rng.choice(vals))
+        if rng.random() < 0.5:
+            parts.append(rng.choice(units))
+        sep = rng.choice([" ", "  ", "\t", " "])
+        line = parts[0] + sep.join(p for p in parts[1:]) + rng.choice(comments)
+        if rng.random() < 0.1:
+            line = "   " + line + "  "
+        try:
+            ref = RefArgInput(line)
+        except Exception as exc:                       # whatever the reference rejects, we must reject too
+            with pytest.raises(type(exc)):
+                ArgInput(line)
+            continue
+        ours = ArgInput(line)
+        same(ours, ref, "parsed", line)
+        new_value = rng.choice(["42", "new value", ("7", True), ("8", False), '"q r"'])
+        ours.value = new_value
+        ref.value = new_value
+        same(ours, ref, "value set", line)
+        if ref.unit is not None:
+            ours.unit = "PSI"
+            ref.unit = "PSI"
+            same(ours, ref, "unit set", line)
+        compared += 1
+    assert compared > 15000

@@ -272,3 +272,73 @@ def test_arg_input_differential_against_reference():
             same(ours, ref, "unit set", line)
         compared += 1
     assert compared > 15000
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/apmapflow"), reason="reference tree not present (GPU box)")
+def test_input_file_differential_updates_clones_and_formats(tmp_path):
+    """Random sequences of update / clone / add_parameter / filename formats on our InputFile and the reference's: the
+    text written to disk, the output file name, the uncommented keys and the format arguments stay identical."""
+    import random
+    sys.path.insert(0, "/root/reference")
+    try:
+        from apmapflow.run_model.run_model import InputFile as RefInputFile
+    except Exception as exc:
+        pytest.skip("reference package not importable: %s" % exc)
+    finally:
+        sys.path.remove("/root/reference")
+    rng = random.Random(7)
+
+    def both(pair, fn):
+        """Applies fn to ours and to the reference's; whatever the reference raises, ours must raise too."""
+        out, errs = [], []
+        for f in pair:
+            try:
+                out.append(fn(f))
+                errs.append(None)
+            except Exception as exc:
+                out.append(None)
+                errs.append(type(exc))
+        assert errs[0] == errs[1], errs
+        return out, errs[0]
+
+    compared = 0
+    for path in ("test-model-inputs.txt", "coverage_test.inp"):
+        for trial in range(60):
+            fmts = {"input_file": os.path.join(str(tmp_path), "{apmap}-{INLET-PRESS}-%d.inp" % trial),
+                    "SUMMARY-FILE": "{apmap}-RF{ROUGHNESS}-log.txt", "VTK-FILE": "out/{apmap}.vtk"}
+            if rng.random() < 0.2:
+                fmts["NO-SUCH-FILE"] = "x.txt"                      # a format for a keyword the file does not have
+            pair = [cls(os.path.join(GOLDEN, path), dict(fmts)) for cls in (InputFile, RefInputFile)]
+            if rng.random() < 0.8:
+                both(pair, lambda f: f.update({"apmap": "m0"}))
+            for step in range(rng.randint(1, 6)):
+                op = rng.choice(["update", "clone", "add", "comment", "str"])
+                if op == "update":
+                    upd = {rng.choice(["INLET-PRESS", "OUTLET-PRESS", "ROUGHNESS", "apmap", "OUTLET-SIDE", "MAP", "new-fmt-arg"]):
+                           rng.choice(["1", "250.5", "TOP", "frac-7", ("9", True), ("3", False)]) for _ in range(rng.randint(1, 3))}
+                    both(pair, lambda f: f.update(upd))
+                elif op == "clone":
+                    clones, err = both(pair, lambda f: f.clone())
+                    if err is None:
+                        pair = clones
+                elif op == "add":
+                    line = rng.choice([";EXTRA-KEY: 5 MM", "EXTRA-KEY: 6 CM ;note", "; a free comment line", "LOW-MASK: 0.5"])
+                    both(pair, lambda f: f.add_parameter(line))
+                elif op == "comment":
+                    key = rng.choice(["OVERWRITE", "INLET-PRESS", "FLUID-VISCOSITY"])
+
+                    def flip(f):
+                        f[key].commented_out = not f[key].commented_out
+                    both(pair, flip)
+                else:
+                    texts, _ = both(pair, str)
+                    assert texts[0] == texts[1]
+            texts, err = both(pair, str)
+            assert texts[0] == texts[1]
+            ours, ref = pair
+            if err is None:
+                assert ours.outfile_name == ref.outfile_name
+                compared += 1
+            assert list(ours.get_uncommented_values()) == list(ref.get_uncommented_values())
+            assert ours.filename_format_args == ref.filename_format_args
+    assert compared > 40

@@ -207,15 +207,18 @@ class InputFile(OrderedDict):
 
 
 def map_dimensions(path, delim="auto"):
-    """(nx, nz) of a text data map without parsing every value."""
-    nz = nx = 0
-    with open(path, "r") as handle:
+    """(nx, nz) of a text data map without converting its values: records are counted (blank and comment-only lines
+    do not count) and only the LAST record is split into fields -- its width is the one the model uses
+    (MAP_MODULE.F:18-85).  A map is read at disk speed; tokenising every line in Python took longer than the solve."""
+    nz, last = 0, None
+    with open(path, "rb") as handle:
         for line in handle:
-            line = line.split(";")[0].strip()
-            if not line:
+            data = line.split(b";", 1)[0].strip()
+            if not data:
                 continue
             nz += 1
-            nx = len([t for t in re.split(r"[\s,=]+", line) if t])
+            last = data
+    nx = len([t for t in re.split(rb"[\s,=]+", last) if t]) if last else 0
     return nx, nz
 
 

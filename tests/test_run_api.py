@@ -62,9 +62,13 @@ def test_input_file_clone_update_formats(tmp_path):      # TestRunCore.py:74-129
     assert again.executable == exe
 
 
-def test_estimate_req_ram():            # TestRunCore.py:131-138
+def test_estimate_req_ram(tmp_path):    # TestRunCore.py:131-138
     path = os.path.join(GOLDEN, "parallel-plate-01vox.txt")
     assert rm.map_dimensions(path) == (100, 100)
+    assert rm.map_dimensions(os.path.join(GOLDEN, "Fracture1ApertureMap-10avg.txt")) == (136, 138)
+    odd = tmp_path / "odd.txt"          # comment-only and blank records do not count, the last record gives the width
+    odd.write_text("; header comment\n\n1, 2, 3 ; trailing\n4\t5\t6\n   \n7=8=9 10\n;end\n")
+    assert rm.map_dimensions(str(odd)) == (4, 3)
     ram = rm.estimate_req_RAM([path], 10)
     assert 0 < ram[0] < 10
     with pytest.raises(EnvironmentError):
